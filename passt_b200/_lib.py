@@ -1,0 +1,99 @@
+"""ctypes binding of libpasst_b200.so (the C ABI declared in include/passt_b200.h).
+
+There is deliberately no CPU / eager fallback: if the library is missing or a kernel fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libpasst_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+vp, i32, f32, f64 = C.c_void_p, C.c_int, C.c_float, C.c_double
+
+_SIGS = {
+    "passt_gemm_debug_desc": (None, [i32, vp]),
+    "passt_gemm_bf16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "passt_mel_workspace_bytes": (C.c_size_t, []),
+    "passt_mel_init": (i32, [vp, i32, vp]),
+    "passt_mel_set_band": (i32, [vp, f64, f64, i32, vp]),
+    "passt_mel_forward": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
+    "passt_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "passt_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "passt_colsum_bf16": (i32, [vp, vp, i32, i32, i32, vp]),
+    "passt_im2col": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "passt_token_table": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "passt_cast_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
+    "passt_head_fwd": (i32, [vp] * 11 + [i32, i32, i32, vp]),
+    "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),
+    "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
+    "passt_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
+}
+
+
+class PasstLibError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is present). Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(_LIB_PATH):
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = f"{what} failed with code {rc}"
+        if rc > 0:
+            msg += " (cudaError)"
+        raise PasstLibError(msg)
+
+
+def call(name: str, *args):
+    fn = getattr(load(), name)
+    rc = fn(*args)
+    check(rc, name)
