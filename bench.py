@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: clips/sec (10 s @ 32 kHz) of a passt_s p16_128 TRAIN step.
+
+Workload (BASELINE.json configs[1]): passt_s, s_patchout_t=40, s_patchout_f=4 (N=474 tokens),
+64 clips per GPU, bf16 tensor-core arithmetic with fp32 master weights / residual stream, synthetic AudioSet-shaped
+data (0.1*randn waveforms, multi-hot 527-class targets), random-init weights.  One step = waveform -> fused mel
+kernel (band augmentation + SpecAugment on) -> patchout-ViT forward -> BCE-with-logits -> hand-written backward
+-> (N>1: NCCL gradient all-reduce) -> AdamW step.  Weak scaling: 64 clips per GPU at every N.
+
+  python bench.py --gpus N --steps K --warmup W          # candidate (sm_100a kernels)
+  python bench.py --impl reference ...                   # the reference algorithm on the host CPU cores (oracle port)
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP_LEN = 320000
+N_CLASSES = 527
+BATCH_PER_GPU = 64
+NET_KW = dict(s_patchout_t=40, s_patchout_f=4)
+WORKLOAD = "passt_s p16_128 s_patchout_t=40 s_patchout_f=4, batch=64/GPU, 10s@32kHz, train step bf16"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def train_flops_per_clip(ntok, depth=12, n_classes=N_CLASSES):
+    fwd = 2 * (ntok - 2) * 256 * 768 + depth * (2 * ntok * 768 * 9216 + 4 * ntok * ntok * 768) + 2 * 768 * n_classes
+    return 3 * fwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ======================================================================================================
+# reference arm: the reference algorithm (CPU oracle port, validated bit-exact against /root/reference) on host cores
+# ======================================================================================================
+def cpu_train_step_rate(sample_clips=2, steps=1, warmup=0):
+    """clips/s of one full train step (mel train-mode + net fwd/bwd + AdamW) of the oracle port on the CPU."""
+    from oracle import passt_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    mcfg, ncfg = O.MelCfg(), O.NetCfg(**NET_KW)
+    params = {k: v.clone().requires_grad_(not k.startswith("head_dist")) for k, v in O.synth_params(ncfg, 0).items()}
+    opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=2e-5, weight_decay=1e-4)
+    torch.manual_seed(0)
+    wave = 0.1 * torch.randn(sample_clips, CLIP_LEN)
+    y = (torch.rand(sample_clips, N_CLASSES) < 0.005).float()
+
+    def step():
+        d = O.draw_mel(mcfg, True, sample_clips)
+        with torch.no_grad():
+            spec = O.mel_frontend(wave, mcfg, d, True).unsqueeze(1)
+        dp = O.draw_patchout(ncfg, 12, 99, True)
+        logits, _ = O.passt_forward(params, spec, ncfg, dp)
+        loss = F.binary_cross_entropy_with_logits(logits, y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_clips * steps / dt, dt / steps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = 2
+    rate, sec = cpu_train_step_rate(sample_clips=sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "clips/sec (10s@32kHz) passt_s p16_128 train step", "value": rate,
+        "unit": "clips/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(args.warmup, 1),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} clips per step on host CPU"},
+        "cpu_baseline": {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample}-clip train step (mel train + fwd + bwd + AdamW), oracle port, fp32"},
+        "e2e": {"value": rate, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# candidate arm
+# ======================================================================================================
+def run_candidate(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from passt_b200 import _lib as L
+    from passt_b200 import engine
+    from passt_b200.passt import get_model
+    from passt_b200.preprocess import AugmentMelSTFT
+    from passt_b200.ddp import GradAllReducer
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py candidate arm needs a CUDA device (sm_100a); there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L.load()
+    peaks = load_peaks()
+    B = BATCH_PER_GPU
+    torch.manual_seed(rank)
+    mel = AugmentMelSTFT(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, freqm=48, timem=192,
+                         fmin=0.0, fmax=None, fmin_aug_range=10, fmax_aug_range=2000).to(dev).train()
+    torch.manual_seed(0)   # identical initial weights on every rank
+    net = get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=N_CLASSES, **NET_KW).to(dev).train()
+    opt = torch.optim.AdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=2e-5,
+                            weight_decay=1e-4, fused=True)
+    reducer = GradAllReducer(net) if world > 1 else None
+    torch.manual_seed(1000 + rank)
+    n_batches = 4
+    host_waves = [(0.1 * torch.randn(B, CLIP_LEN)).pin_memory() for _ in range(n_batches)]
+    dev_waves = [w.to(dev) for w in host_waves]
+    y = (torch.rand(B, N_CLASSES, device=dev) < 0.005).float()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def train_step(wave_dev):
+        with torch.no_grad():
+            spec = mel(wave_dev).unsqueeze(1)
+        logits, _ = net(spec)
+        loss = F.binary_cross_entropy_with_logits(logits, y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.all_reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up
+    for i in range(max(3, args.warmup)):
+        train_step(dev_waves[i % n_batches])
+    barrier()
+    ntok = net.last_plan.ntok
+
+    # ---- (1) device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.reset_launch_count()
+    ms_dev = timed(lambda i: train_step(dev_waves[i % n_batches]), args.steps)
+    launches = L.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- (2) end to end: pinned host waveform -> H2D -> step -> D2H loss, every step
+    def e2e_step(i):
+        w = host_waves[i % n_batches].to(dev, non_blocking=True)
+        loss = train_step(w)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- (3) roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every GEMM launch in a
+    #          repeat of the timed steps (kept out of the headline timing so the events do not perturb it)
+    engine.GEMM_TRACE = []
+    ms_instr = timed(lambda i: train_step(dev_waves[i % n_batches]), args.steps)
+    torch.cuda.synchronize()
+    trace, engine.GEMM_TRACE = engine.GEMM_TRACE, None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in trace)
+    gemm_flops = sum(f for _, _, f in trace)
+    n_gemm = max(1, len(trace))
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = peaks["bf16_sustained"]
+
+    total_clips = B * world * args.steps
+    value = total_clips / (ms_dev * 1e-3)
+    e2e_value = total_clips / (ms_e2e * 1e-3)
+    step_flops = train_flops_per_clip(ntok) * B
+
+    line = None
+    if rank == 0:
+        cpu_rate, cpu_sec = cpu_train_step_rate(sample_clips=2, steps=1, warmup=0) if world == 1 else (None, None)
+        line = {
+            "metric": "clips/sec (10s@32kHz) passt_s p16_128 train step", "value": value, "unit": "clips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tokens": ntok, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "optimizer": "AdamW(fused) fp32 master weights", "loss": "BCE-with-logits, 527 classes",
+                       "l2": "4 rotating input batches; per-step working set (~10 GB of activations) >> 126 MB L2",
+                       "model_flops_per_step": step_flops,
+                       "model_tflops": step_flops * world / (ms_dev / args.steps * 1e-3) / 1e12},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * CLIP_LEN * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "gemm_kernel<BN,MODE> (tcgen05 GEMM family: fwd, dgrad, wgrad)", "bound": "tensor",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                         "launches_per_step": n_gemm / args.steps, "avg_launch_ms": gemm_ms / n_gemm,
+                         "share_of_step": gemm_ms / ms_instr if ms_instr else None,
+                         "how": "CUDA events around each GEMM launch in a repeat of the timed steps"},
+        }
+        if cpu_rate is not None:
+            line["cpu_baseline"] = {"value": cpu_rate, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "one 2-clip train step (mel + fwd + bwd + AdamW) of the CPU oracle port, fp32"}
+        print(json.dumps(line), flush=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="candidate", choices=["candidate", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_candidate(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

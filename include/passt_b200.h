@@ -1,0 +1,87 @@
+/* passt_b200 — C ABI of the sm_100a kernel library (passt_b200/lib/libpasst_b200.so).
+ *
+ * The reference (kkoutini/PaSST) has no FFI: its hot path is Python calling torch / torchaudio ops.  Each entry
+ * point below replaces the torch op sequence cited next to it; the Python modules in passt_b200/ (drop-ins for
+ * models/preprocess.py and models/passt.py) are the only callers.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions: plain device pointers + sizes, no torch types; all calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*); return 0 on success, a positive cudaError_t, or a negative library code
+ * (-2 bad argument, -3 driver/tensor-map failure).  bf16 tensors are passed as `void*`.
+ */
+#ifndef PASST_B200_H
+#define PASST_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- frontend: AugmentMelSTFT.forward, reference models/preprocess.py:57-86 --------------------------------- */
+/* bytes of device scratch holding the hann/twiddle tables and the sparse mel filterbank */
+size_t passt_mel_workspace_bytes(void);
+/* hann(win_length, periodic=False) centred in n_fft=1024 + FFT twiddles (preprocess.py:38-40) */
+int passt_mel_init(void* workspace, int win_length, void* stream);
+/* kaldi triangular filterbank for (fmin, fmax) built ON DEVICE (preprocess.py:71-74; torchaudio kaldi.py:436-511) */
+int passt_mel_set_band(void* workspace, double fmin, double fmax, int sample_rate, void* stream);
+/* wave f32 [B,L] -> log-mel f32 [B,128,T], T = 1+(L-1)/hop.  rnd: f32 [4,B] SpecAugment uniforms or NULL (eval);
+ * pre-emphasis :59, STFT :60-61, power :62, mel matmul :76, log :78, freq/time masking :80-82, affine :84 */
+int passt_mel_forward(const void* workspace, const float* wave, float* out, int B, int L, int hop, const float* rnd,
+                      int freqm, int timem, void* stream);
+
+/* ---- tcgen05 GEMM family: nn.Linear fwd/bwd (models/passt.py:279-289, :338-359) and PatchEmbed.proj (:315) ---- */
+/* mode 0: C[M,N] = bf16(A[M,K] B[N,K]^T + bias)            (A,B,C bf16; K-major operands)
+ * mode 1: C = bf16(acc + bias), C2 = bf16(gelu(acc + bias)) (Mlp.fc1 + nn.GELU, :285-286)
+ * mode 2: C f32 = acc + aux_f32[row % aux_period, :]        (patch-embed: bias + pos-embeds + cls/dist rows)
+ * mode 3: C = bf16(acc * gelu'(aux_bf16[row, :]))           (fc2 dgrad fused with GELU backward)
+ * mode 4: C f32 [M,N] += A[K,M]^T B[K,N]                    (weight gradient; split-K, TMA reduce-add)      */
+int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
+                    int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,
+                    int max_ctas, void* stream);
+/* bring-up hook: override the UMMA shared-memory descriptor strides (6 uint32); active=0 restores defaults */
+void passt_gemm_debug_desc(int active, const unsigned* v6);
+
+/* ---- attention: softmax(q k^T * scale) v, models/passt.py:345-358, and its autograd ---------------------------- */
+/* qkv bf16 [B,N,3*H*64] (layout of nn.Linear(dim,3*dim) output, :345) -> out bf16 [B,N,H*64], lse f32 [B,H,N] */
+int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream);
+size_t passt_attn_bwd_workspace_bytes(int B, int N, int H);
+int passt_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
+                   void* workspace, int B, int N, int H, float scale, void* stream);
+
+/* ---- row kernels ------------------------------------------------------------------------------------------------ */
+/* x_out = x_in (+ delta); h = LayerNorm(x_out) (Block residual + norm1/norm2, models/passt.py:377-380) */
+int passt_ln_fwd(const float* x_in, const void* delta_bf16, float* x_out, void* h_bf16, float* mean, float* rstd,
+                 const float* gamma, const float* beta, int M, int dim, float eps, void* stream);
+/* g_out = g_in + dLN(dh); bf16 copy; dgamma/dbeta/colsum accumulate (+=) */
+int passt_ln_bwd(const void* dh_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                 const float* g_in, float* g_out, void* g_out_bf16, float* dgamma, float* dbeta, float* colsum,
+                 int M, int dim, void* stream);
+/* out[n] += sum_m in[m,n]  (bias gradients) */
+int passt_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, void* stream);
+/* kept 16x16 patches of mel f32 [B,Fm,Tm] -> bf16 rows [B*ntok,256]; rows 0,1 of each clip are zero (cls/dist);
+ * optional fused spectrogram mixup (ex_audioset.py:173-177).  Patchout gathers of models/passt.py:535-552. */
+int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* patch_t, int B, int ntok, int Fm,
+                 int Tm, int fstride, int tstride, const int* mix_perm, const float* mix_lam, void* stream);
+/* additive token table: conv bias + time/freq pos-embed (models/passt.py:527-529), cls/dist rows (:557-564) */
+int passt_token_table(float* tab, const float* cls, const float* dist, const float* new_pos,
+                      const float* conv_bias, const float* time_pos, const float* freq_pos, const int* patch_f,
+                      const int* patch_t, int ntok, int Fg, int Tg, int toff, void* stream);
+int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dnew_pos, float* dconv_bias,
+                          float* dtime, float* dfreq, const int* patch_f, const int* patch_t, int B, int ntok,
+                          int Fg, int Tg, int toff, void* stream);
+/* f32 [R,C] -> bf16 [R,C] and bf16 [C,R] (tensor-core operand copies of the fp32 master weights) */
+int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R, int C, void* stream);
+/* final norm on cls/dist rows, (cls+dist)/2, head LayerNorm + Linear (models/passt.py:570-588, :463-464) */
+int passt_head_fwd(const float* x, const void* delta_bf16, const float* norm_g, const float* norm_b,
+                   const float* hln_g, const float* hln_b, const float* W, const float* bias, float* logits,
+                   float* features, float* fl, int B, int ntok, int C, void* stream);
+int passt_head_bwd(const float* x, const void* delta_bf16, const float* norm_g, const float* norm_b,
+                   const float* hln_g, const float* hln_b, const float* W, const float* dlogits,
+                   const float* dfeatures, const float* fl, float* g_out, void* g_out_bf16, float* d_norm_g,
+                   float* d_norm_b, float* d_hln_g, float* d_hln_b, float* dW, float* dbias, float* colsum, int B,
+                   int ntok, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASST_B200_H */

@@ -35,6 +35,7 @@ _SIGS = {
     "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),
     "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "passt_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
+    "passt_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
 }
 
 
@@ -93,7 +94,24 @@ def check(rc: int, what: str):
         raise PasstLibError(msg)
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+_LAUNCHES = {"passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
+             "passt_attn_bwd_workspace_bytes": 0}
+_launch_counter = 0
+
+
+def reset_launch_count():
+    global _launch_counter
+    _launch_counter = 0
+
+
+def launch_count() -> int:
+    return _launch_counter
+
+
 def call(name: str, *args):
+    global _launch_counter
     fn = getattr(load(), name)
     rc = fn(*args)
     check(rc, name)
+    _launch_counter += _LAUNCHES.get(name, 1)

@@ -80,8 +80,8 @@ ln_fwd_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ 
 constexpr int kLnBwdWarps = 8;
 __global__ void __launch_bounds__(kLnBwdWarps * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ g_in,
-              float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* g_in,
+              float* g_out, __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ colsum, int M, int rows_per_cta) {
   __shared__ float red[kLnBwdWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,0 +1,341 @@
+"""Host-side orchestration of the sm_100a kernels for one PaSST forward/backward.
+
+This is plumbing only: it owns no arithmetic.  Every tensor op on the path is a call into libpasst_b200.so
+(include/passt_b200.h) on torch's current CUDA stream; torch supplies device memory and autograd glue.
+
+Reference being replaced: PaSST.forward_features / forward (models/passt.py:506-595), Block / Attention / Mlp
+(:271-380) and their autograd.  Random draws (time-embedding offset :516, structured patchout :535/:541,
+unstructured patchout :551) are made here with the *same torch CPU-generator calls in the same order* so that
+patchout indices are bit-identical to the reference for a given seed.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class StepPlan:
+    """Everything one forward pass needs that is decided on the host."""
+    B: int
+    ntok: int                 # tokens per clip including cls + dist
+    Fm: int                   # mel bins of the input
+    Tm: int                   # mel frames of the input
+    toffset: int
+    patch_f: torch.Tensor     # int32 [ntok-2] device: freq grid row of each kept patch
+    patch_t: torch.Tensor     # int32 [ntok-2] device: time grid column of each kept patch
+    t_keep: Optional[torch.Tensor] = None   # CPU int64 draws (exposed for parity tests)
+    f_keep: Optional[torch.Tensor] = None
+    u_keep: Optional[torch.Tensor] = None
+
+
+def draw_step_plan(net, x: torch.Tensor, training: bool) -> StepPlan:
+    """Host RNG + index bookkeeping of forward_features (models/passt.py:508-553)."""
+    B, Cin, Fm, Tm = x.shape
+    ps, (fs, ts) = net.patch_size, net.stride
+    f_dim = (Fm - ps) // fs + 1                       # Conv2d output size (:315)
+    t_dim = (Tm - ps) // ts + 1
+    Fg, Tg = net.patch_embed.grid_size
+    if f_dim != Fg:
+        raise RuntimeError(f"input has {f_dim} patch rows but the frequency embedding has {Fg} (passt.py:529)")
+    toffset = 0
+    if t_dim < Tg:
+        if training:
+            toffset = int(torch.randint(1 + Tg - t_dim, (1,)).item())       # (:516)
+    else:
+        t_dim = Tg                                                          # x is cut to the embedding (:523-526)
+    t_idx = torch.arange(t_dim)
+    f_idx = torch.arange(f_dim)
+    t_keep = f_keep = u_keep = None
+    if training and net.s_patchout_t:
+        t_keep = torch.randperm(t_dim)[: t_dim - net.s_patchout_t].sort().values   # (:535)
+        t_idx = t_keep
+    if training and net.s_patchout_f:
+        f_keep = torch.randperm(f_dim)[: f_dim - net.s_patchout_f].sort().values   # (:541)
+        f_idx = f_keep
+    # flatten(2): F-major, T-minor token order (:546)
+    pf = f_idx.repeat_interleave(len(t_idx))
+    pt = t_idx.repeat(len(f_idx))
+    if training and net.u_patchout:
+        seq = pf.numel()
+        u_keep = torch.randperm(seq)[: seq - net.u_patchout].sort().values         # (:551)
+        pf, pt = pf[u_keep], pt[u_keep]
+    host = torch.stack([pf, pt]).to(torch.int32)
+    if x.is_cuda:
+        host = host.pin_memory()
+    dev = host.to(x.device, non_blocking=True)
+    return StepPlan(B=B, ntok=pf.numel() + 2, Fm=Fm, Tm=Tm, toffset=toffset, patch_f=dev[0], patch_t=dev[1],
+                    t_keep=t_keep, f_keep=f_keep, u_keep=u_keep)
+
+
+class WeightCache:
+    """bf16 copies of the fp32 master weights: W [out,in] for fwd/wgrad and W^T [in,out] for dgrad.
+    Refreshed by one cast_transpose kernel per matrix whenever the parameter changed (optimizer step)."""
+
+    def __init__(self):
+        self._store: Dict[int, tuple] = {}
+
+    def get(self, p: torch.Tensor, need_t: bool):
+        key = (p.data_ptr(), tuple(p.shape))
+        ent = self._store.get(key)
+        ver = (p.data_ptr(), p._version)
+        if ent is not None and ent[0] == ver and (ent[2] is not None or not need_t):
+            return ent[1], ent[2]
+        w2 = p.detach().reshape(p.shape[0], -1)
+        R, C = w2.shape
+        wb = ent[1] if ent is not None and ent[1].device == p.device else torch.empty(R, C, dtype=BF16, device=p.device)
+        wt = None
+        if need_t:
+            wt = ent[2] if ent is not None and ent[2] is not None and ent[2].device == p.device else \
+                torch.empty(C, R, dtype=BF16, device=p.device)
+        L.call("passt_cast_transpose", L.ptr(w2), L.ptr(wb), L.ptr(wt), R, C, L.stream_ptr())
+        self._store[key] = (ver, wb, wt)
+        return wb, wt
+
+    def clear(self):
+        self._store.clear()
+
+
+GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
+
+
+def _gemm(A, Bm, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, mode, period=0, ld_aux=0, splits=1):
+    if GEMM_TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("passt_gemm_bf16", L.ptr(A), L.ptr(Bm), L.ptr(C), L.ptr(C2), L.ptr(bias), L.ptr(aux), M, N, K, lda, ldb,
+           ldc, mode, period, ld_aux, splits, 0, L.stream_ptr())
+    if GEMM_TRACE is not None:
+        e1.record()
+        GEMM_TRACE.append((e0, e1, 2.0 * M * N * K))
+
+
+def _wgrad_splits(M_out: int, N_out: int, tokens: int) -> int:
+    tiles = (M_out // 128) * (N_out // 256)
+    kb = (tokens + 63) // 64
+    s = max(1, min(kb, (4 * 148 + tiles - 1) // tiles))
+    return s
+
+
+PARAM_ORDER_HEAD = ["cls_token", "dist_token", "new_pos_embed", "freq_new_pos_embed", "time_new_pos_embed",
+                    "patch_embed.proj.weight", "patch_embed.proj.bias"]
+PARAM_ORDER_BLOCK = ["norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
+                     "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                     "mlp.fc2.weight", "mlp.fc2.bias"]
+PARAM_ORDER_TAIL = ["norm.weight", "norm.bias", "head.0.weight", "head.0.bias", "head.1.weight", "head.1.bias"]
+
+
+def param_names(depth: int) -> List[str]:
+    names = list(PARAM_ORDER_HEAD)
+    for i in range(depth):
+        names += [f"blocks.{i}.{n}" for n in PARAM_ORDER_BLOCK]
+    return names + PARAM_ORDER_TAIL
+
+
+class PasstFunction(torch.autograd.Function):
+    """(mel image, *params) -> (logits, features).  Saves bf16 activations for the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, x, net, plan: StepPlan, mix, *params):
+        if not x.is_cuda:
+            raise RuntimeError("passt_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        dev = x.device
+        names = param_names(len(net.blocks))
+        P = dict(zip(names, params))
+        depth, Dm, H = len(net.blocks), net.embed_dim, net.num_heads
+        hidden = P["blocks.0.mlp.fc1.weight"].shape[0] if depth else 4 * Dm
+        B, ntok = plan.B, plan.ntok
+        M = B * ntok
+        Fg, Tg = net.patch_embed.grid_size
+        fs, ts = net.stride
+        need_grad = any(ctx.needs_input_grad[4:])   # Function.forward itself runs with grad mode off
+        wc: WeightCache = net._wcache
+        st = L.stream_ptr()
+        x32 = x.detach()
+        if x32.dtype != torch.float32:
+            x32 = x32.float()
+        x32 = x32.contiguous()
+        if x32.shape[1] != 1:
+            raise RuntimeError("passt_b200 supports in_channels == 1 (mono spectrograms)")
+        f32 = dict(device=dev, dtype=torch.float32)
+        b16 = dict(device=dev, dtype=BF16)
+
+        # ---- patch embedding: im2col of kept patches -> GEMM + token table (bias + pos embeds + cls/dist rows)
+        A0 = torch.empty(M, 256, **b16)
+        mix_perm = mix_lam = None
+        if mix is not None:
+            mix_perm, mix_lam = mix
+        L.call("passt_im2col", L.ptr(x32), L.ptr(A0), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, plan.Fm,
+               plan.Tm, fs, ts, L.ptr(mix_perm), L.ptr(mix_lam), st)
+        tab = torch.empty(ntok, Dm, **f32)
+        L.call("passt_token_table", L.ptr(tab), L.ptr(P["cls_token"]), L.ptr(P["dist_token"]),
+               L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
+               L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset, st)
+        wpe, _ = wc.get(P["patch_embed.proj.weight"], False)
+        xcur = torch.empty(M, Dm, **f32)
+        _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
+
+        saved = []
+        delta = None
+        scale = float((Dm // H) ** -0.5)
+        for i in range(depth):
+            pre = f"blocks.{i}."
+            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], need_grad)
+            wproj, _ = wc.get(P[pre + "attn.proj.weight"], need_grad)
+            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], need_grad)
+            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], need_grad)
+            # x_in = xcur (+ delta of the previous block); h1 = LN1(x_in)
+            h1 = torch.empty(M, Dm, **b16)
+            mean1 = torch.empty(M, **f32); rstd1 = torch.empty(M, **f32)
+            if delta is None:
+                x_in = xcur
+                L.call("passt_ln_fwd", L.ptr(x_in), None, None, L.ptr(h1), L.ptr(mean1), L.ptr(rstd1),
+                       L.ptr(P[pre + "norm1.weight"]), L.ptr(P[pre + "norm1.bias"]), M, Dm, 1e-6, st)
+            else:
+                x_in = torch.empty(M, Dm, **f32)
+                L.call("passt_ln_fwd", L.ptr(xcur), L.ptr(delta), L.ptr(x_in), L.ptr(h1), L.ptr(mean1), L.ptr(rstd1),
+                       L.ptr(P[pre + "norm1.weight"]), L.ptr(P[pre + "norm1.bias"]), M, Dm, 1e-6, st)
+            qkv = torch.empty(M, 3 * Dm, **b16)
+            _gemm(h1, wqkv, qkv, bias=P[pre + "attn.qkv.bias"], M=M, N=3 * Dm, K=Dm, lda=Dm, ldb=Dm, ldc=3 * Dm, mode=0)
+            att = torch.empty(M, Dm, **b16)
+            lse = torch.empty(B, H, ntok, **f32)
+            L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(att), L.ptr(lse), B, ntok, H, scale, st)
+            oproj = torch.empty(M, Dm, **b16)
+            _gemm(att, wproj, oproj, bias=P[pre + "attn.proj.bias"], M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)
+            x_mid = torch.empty(M, Dm, **f32)
+            h2 = torch.empty(M, Dm, **b16)
+            mean2 = torch.empty(M, **f32); rstd2 = torch.empty(M, **f32)
+            L.call("passt_ln_fwd", L.ptr(x_in), L.ptr(oproj), L.ptr(x_mid), L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
+                   L.ptr(P[pre + "norm2.weight"]), L.ptr(P[pre + "norm2.bias"]), M, Dm, 1e-6, st)
+            pre_act = torch.empty(M, hidden, **b16)
+            act = torch.empty(M, hidden, **b16)
+            _gemm(h2, wfc1, pre_act, C2=act, bias=P[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm, ldb=Dm,
+                  ldc=hidden, mode=1)
+            ofc2 = torch.empty(M, Dm, **b16)
+            _gemm(act, wfc2, ofc2, bias=P[pre + "mlp.fc2.bias"], M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden, ldc=Dm,
+                  mode=0)
+            if need_grad:
+                saved.append(dict(x_in=x_in, mean1=mean1, rstd1=rstd1, h1=h1, qkv=qkv, att=att, lse=lse, x_mid=x_mid,
+                                  mean2=mean2, rstd2=rstd2, h2=h2, pre_act=pre_act, act=act))
+            xcur, delta = x_mid, ofc2
+
+        C = P["head.1.weight"].shape[0]
+        logits = torch.empty(B, C, **f32)
+        feats = torch.empty(B, Dm, **f32)
+        fl = torch.empty(B, Dm, **f32)
+        L.call("passt_head_fwd", L.ptr(xcur), L.ptr(delta), L.ptr(P["norm.weight"]), L.ptr(P["norm.bias"]),
+               L.ptr(P["head.0.weight"]), L.ptr(P["head.0.bias"]), L.ptr(P["head.1.weight"]), L.ptr(P["head.1.bias"]),
+               L.ptr(logits), L.ptr(feats), L.ptr(fl), B, ntok, C, st)
+        if need_grad:
+            ctx.net = net
+            ctx.plan = plan
+            ctx.names = names
+            ctx.params = params
+            ctx.saved = saved
+            ctx.misc = dict(A0=A0, x_last=xcur, delta_last=delta, fl=fl, M=M, hidden=hidden, C=C, scale=scale)
+        return logits, feats
+
+    @staticmethod
+    def backward(ctx, dlogits, dfeats):
+        net, plan, names, params = ctx.net, ctx.plan, ctx.names, ctx.params
+        P = dict(zip(names, params))
+        mi = ctx.misc
+        M, hidden, C, scale = mi["M"], mi["hidden"], mi["C"], mi["scale"]
+        depth, Dm, H = len(net.blocks), net.embed_dim, net.num_heads
+        B, ntok = plan.B, plan.ntok
+        Fg, Tg = net.patch_embed.grid_size
+        dev = mi["x_last"].device
+        st = L.stream_ptr()
+        wc: WeightCache = net._wcache
+        f32 = dict(device=dev, dtype=torch.float32)
+        b16 = dict(device=dev, dtype=BF16)
+
+        # one flat, zero-initialised fp32 gradient buffer; each parameter's gradient is a view into it
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), **f32)
+        G, off, span = {}, 0, {}
+        for n, p, s in zip(names, params, sizes):
+            G[n] = flat[off: off + s].view(p.shape)
+            span[n] = (off, off + s)
+            off += s
+        hook = getattr(net, "_grad_chunk_hook", None)
+
+        def chunk_done(first: str, last: str):
+            if hook is not None:
+                hook(flat, span[first][0], span[last][1])
+
+        dl = None if dlogits is None else dlogits.detach().float().contiguous()
+        df = None if dfeats is None else dfeats.detach().float().contiguous()
+        if dl is None:
+            dl = torch.zeros(B, C, **f32)
+        g = torch.zeros(M, Dm, **f32)
+        gb = torch.zeros(M, Dm, **b16)
+        last_bias = G[f"blocks.{depth - 1}.mlp.fc2.bias"] if depth else None
+        L.call("passt_head_bwd", L.ptr(mi["x_last"]), L.ptr(mi["delta_last"]), L.ptr(P["norm.weight"]),
+               L.ptr(P["norm.bias"]), L.ptr(P["head.0.weight"]), L.ptr(P["head.0.bias"]), L.ptr(P["head.1.weight"]),
+               L.ptr(dl), L.ptr(df), L.ptr(mi["fl"]), L.ptr(g), L.ptr(gb), L.ptr(G["norm.weight"]), L.ptr(G["norm.bias"]),
+               L.ptr(G["head.0.weight"]), L.ptr(G["head.0.bias"]), L.ptr(G["head.1.weight"]), L.ptr(G["head.1.bias"]),
+               L.ptr(last_bias), B, ntok, C, st)
+        chunk_done("norm.weight", "head.1.bias")
+
+        ws_bytes = L.load().passt_attn_bwd_workspace_bytes(B, ntok, H)
+        attn_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dact = torch.empty(M, hidden, **b16)
+        dh = torch.empty(M, Dm, **b16)
+        datt = torch.empty(M, Dm, **b16)
+        dqkv = torch.empty(M, 3 * Dm, **b16)
+        for i in reversed(range(depth)):
+            pre = f"blocks.{i}."
+            S = ctx.saved[i]
+            _, wqkv_t = wc.get(P[pre + "attn.qkv.weight"], True)
+            _, wproj_t = wc.get(P[pre + "attn.proj.weight"], True)
+            _, wfc1_t = wc.get(P[pre + "mlp.fc1.weight"], True)
+            _, wfc2_t = wc.get(P[pre + "mlp.fc2.weight"], True)
+            # ---- MLP
+            _gemm(gb, wfc2_t, dact, aux=S["pre_act"], M=M, N=hidden, K=Dm, lda=Dm, ldb=Dm, ldc=hidden, mode=3,
+                  ld_aux=hidden)                                           # d pre = (g W2) * gelu'(pre)
+            _gemm(gb, S["act"], G[pre + "mlp.fc2.weight"], M=Dm, N=hidden, K=M, lda=Dm, ldb=hidden, ldc=hidden,
+                  mode=4, splits=_wgrad_splits(Dm, hidden, M))
+            _gemm(dact, wfc1_t, dh, M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden, ldc=Dm, mode=0)
+            _gemm(dact, S["h2"], G[pre + "mlp.fc1.weight"], M=hidden, N=Dm, K=M, lda=hidden, ldb=Dm, ldc=Dm, mode=4,
+                  splits=_wgrad_splits(hidden, Dm, M))
+            L.call("passt_colsum_bf16", L.ptr(dact), L.ptr(G[pre + "mlp.fc1.bias"]), M, hidden, hidden, st)
+            L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_mid"]), L.ptr(S["mean2"]), L.ptr(S["rstd2"]),
+                   L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm2.weight"]),
+                   L.ptr(G[pre + "norm2.bias"]), L.ptr(G[pre + "attn.proj.bias"]), M, Dm, st)
+            # ---- attention
+            _gemm(gb, wproj_t, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)
+            _gemm(gb, S["att"], G[pre + "attn.proj.weight"], M=Dm, N=Dm, K=M, lda=Dm, ldb=Dm, ldc=Dm, mode=4,
+                  splits=_wgrad_splits(Dm, Dm, M))
+            L.call("passt_attn_bwd", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
+                   L.ptr(attn_ws), B, ntok, H, scale, st)
+            _gemm(dqkv, wqkv_t, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=3 * Dm, ldc=Dm, mode=0)
+            _gemm(dqkv, S["h1"], G[pre + "attn.qkv.weight"], M=3 * Dm, N=Dm, K=M, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=4,
+                  splits=_wgrad_splits(3 * Dm, Dm, M))
+            L.call("passt_colsum_bf16", L.ptr(dqkv), L.ptr(G[pre + "attn.qkv.bias"]), M, 3 * Dm, 3 * Dm, st)
+            prev_bias = G[f"blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else None
+            L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_in"]), L.ptr(S["mean1"]), L.ptr(S["rstd1"]),
+                   L.ptr(P[pre + "norm1.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm1.weight"]),
+                   L.ptr(G[pre + "norm1.bias"]), L.ptr(prev_bias), M, Dm, st)
+            ctx.saved[i] = None
+            # every gradient of block i is final except mlp.fc2.bias of block i-1 (written above into ITS span)
+            chunk_done(pre + "norm1.weight", pre + "mlp.fc2.bias")
+        # ---- patch embedding
+        gpe = G["patch_embed.proj.weight"].view(Dm, 256)
+        _gemm(gb, mi["A0"], gpe, M=Dm, N=256, K=M, lda=Dm, ldb=256, ldc=256, mode=4, splits=_wgrad_splits(Dm, 256, M))
+        L.call("passt_token_table_bwd", L.ptr(g), L.ptr(G["cls_token"]), L.ptr(G["dist_token"]),
+               L.ptr(G["new_pos_embed"]), L.ptr(G["patch_embed.proj.bias"]), L.ptr(G["time_new_pos_embed"]),
+               L.ptr(G["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, Fg, Tg,
+               plan.toffset, st)
+        chunk_done("cls_token", "patch_embed.proj.bias")
+        net._last_flat_grad = flat
+        ctx.saved = None
+        ctx.misc = None
+        grads = [G[n] if p.requires_grad else None for n, p in zip(names, params)]
+        return (None, None, None, None, *grads)

@@ -280,6 +280,50 @@ def g_rowops():
         cs=relerr(cs, goutb.float().sum((0, 1))))
 
 
+def g_attn():
+    torch.manual_seed(4)
+    H, hd = 12, 64
+    C = H * hd
+    scale = hd ** -0.5
+    for (B, N) in [(2, 128), (2, 130), (2, 474), (1, 1190), (64, 474)]:
+        qkv = (torch.randn(B, N, 3 * C, device=dev)).bfloat16()
+        out = torch.full((B, N, C), float("nan"), device=dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, N, device=dev)
+        L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, scale, L.stream_ptr())
+        torch.cuda.synchronize()
+        rec = dict(test="attn_fwd", B=B, N=N)
+        if B <= 2:
+            x = qkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+            q, k, v = [t.clone().requires_grad_(True) for t in (x[0], x[1], x[2])]
+            att = (q @ k.transpose(-2, -1)) * scale
+            ref_lse = torch.logsumexp(att, -1)
+            ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+            rec.update(o=relerr(out, ref), lse=relerr(lse, ref_lse), nan=int(torch.isnan(out.float()).sum()))
+        else:
+            ms = timeit(lambda: L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, scale, L.stream_ptr()))
+            rec.update(ms=ms, tflops=4.0 * B * H * N * N * hd / ms / 1e9)
+        log(**rec)
+        # backward
+        dO = (torch.randn(B, N, C, device=dev)).bfloat16()
+        dqkv = torch.full((B, N, 3 * C), float("nan"), device=dev, dtype=torch.bfloat16)
+        wsb = L.load().passt_attn_bwd_workspace_bytes(B, N, H)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(ws), B, N, H, scale,
+               L.stream_ptr())
+        torch.cuda.synchronize()
+        rec = dict(test="attn_bwd", B=B, N=N)
+        if B <= 2:
+            ref.backward(dO.float())
+            g = dqkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+            rec.update(dq=relerr(g[0], q.grad), dk=relerr(g[1], k.grad), dv=relerr(g[2], v.grad),
+                       nan=int(torch.isnan(dqkv.float()).sum()))
+        else:
+            ms = timeit(lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv),
+                                       L.ptr(ws), B, N, H, scale, L.stream_ptr()))
+            rec.update(ms=ms, tflops=10.0 * B * H * N * N * hd / ms / 1e9)
+        log(**rec)
+
+
 GROUPS = {k[2:]: v for k, v in globals().items() if k.startswith("g_")}
 
 if __name__ == "__main__":

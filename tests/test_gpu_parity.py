@@ -1,0 +1,166 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in modules) against the CPU oracle on the same
+seeded inputs.  Tolerances: mel 1e-4 abs on the normalised log-mel (fp32 kernel); network in bf16 tensor-core
+arithmetic: 1e-2 relative (max-abs error / max-abs reference) per north_star; patchout indices bit-exact."""
+import os
+
+import pytest
+import torch
+
+from util import build_net, quiet, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _oracle():
+    from oracle import passt_oracle as O
+    return O
+
+
+@pytest.mark.parametrize("training", [False, True])
+@pytest.mark.parametrize("L", [320000, 160000, 33000])
+def test_mel_parity(training, L):
+    O = _oracle()
+    from passt_b200.preprocess import AugmentMelSTFT
+    cfg = O.MelCfg()
+    with quiet():
+        mel = AugmentMelSTFT(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, freqm=48, timem=192,
+                             fmin=0.0, fmax=None, fmin_aug_range=10, fmax_aug_range=2000).to(DEV)
+    mel.train(training)
+    torch.manual_seed(11)
+    wave = 0.1 * torch.randn(3, L)
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    out = mel(wave.to(DEV))
+    fmin, fmax, rnd = mel.last_draws
+    d = O.StepDraws(fmin=fmin, fmax=fmax, mask_rnd=None if rnd is None else rnd.cpu())
+    # CPU-generator draw order must match the oracle's restatement of the reference
+    torch.manual_seed(5)
+    d2 = O.draw_mel(cfg, training, 3)
+    assert (d2.fmin, d2.fmax) == (fmin, fmax)
+    ref = O.mel_frontend(wave, cfg, d, training)
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max().item() < 1e-4
+    if training:
+        assert (out == 0.9).any()      # masked cells: (0 + 4.5) / 5
+
+
+def _run_candidate(net, x, training, seed):
+    net.train(training)
+    torch.manual_seed(seed)
+    logits, feats = net(x)
+    return logits, feats
+
+
+@pytest.mark.parametrize("kw,training", [
+    (dict(), False),
+    (dict(s_patchout_t=40, s_patchout_f=4), True),
+    (dict(u_patchout=400), True),
+    (dict(s_patchout_t=10, s_patchout_f=3, n_classes=50), True),
+])
+def test_net_forward_backward_parity_depth2(kw, training):
+    """2-block network (lighten_model cut_depth=10): logits, features, indices and every parameter gradient."""
+    O = _oracle()
+    T = 500 if kw.get("n_classes") == 50 else 1000
+    cfg12 = O.NetCfg(**kw)
+    params12 = O.synth_params(cfg12, seed=3)
+    net = build_net(cfg12, params12, DEV, cut_depth=10)
+    # oracle params for the 2 remaining blocks: block 0 and block 11 -> renumbered 0,1
+    cfg = O.NetCfg(depth=2, **kw)
+    p = {}
+    for k, v in params12.items():
+        if k.startswith("blocks."):
+            i = int(k.split(".")[1])
+            if i == 0:
+                p[k] = v
+            elif i == 11:
+                p[k.replace("blocks.11.", "blocks.1.")] = v
+        else:
+            p[k] = v
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    torch.manual_seed(21)
+    B = 2
+    x = torch.randn(B, 1, 128, T)
+    logits, feats = _run_candidate(net, x.to(DEV), training, seed=9)
+    torch.manual_seed(9)
+    d = O.draw_patchout(cfg, 12, (T - 16) // 10 + 1, training)
+    plan = net.last_plan
+    # bit-exact patchout indices
+    for a, b in ((plan.t_keep, d.t_keep), (plan.f_keep, d.f_keep), (plan.u_keep, d.u_keep)):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b)
+    assert plan.toffset == d.toffset
+    ref_logits, ref_feats = O.passt_forward(p, x, cfg, d)
+    assert relerr(logits, ref_logits) < 1e-2
+    assert relerr(feats, ref_feats) < 1e-2
+    if not training:
+        return
+    torch.manual_seed(33)
+    w = torch.randn_like(ref_logits)
+    (ref_logits * w).sum().backward()
+    (logits * w.to(DEV)).sum().backward()
+    got = dict(net.named_parameters())
+    bad = []
+    for k, v in p.items():
+        kk = k
+        if k.startswith("blocks.1."):
+            kk = k  # Sequential re-indexes
+        g = got[kk].grad
+        if k.startswith("head_dist"):
+            assert g is None or float(g.abs().max()) == 0.0      # unused in forward (passt.py:582-588)
+            continue
+        assert g is not None, k
+        e = relerr(g, v.grad)
+        if e > 2e-2:
+            bad.append((k, e))
+    assert not bad, bad
+
+
+def test_cfg1_full_depth_eval_logit_parity():
+    """BASELINE config 1: passt_s_swa_p16_128_ap476 forward, batch 2, 10 s clips through mel + net."""
+    O = _oracle()
+    from passt_b200.wrapper import PasstBasicWrapper
+    from passt_b200.preprocess import AugmentMelSTFT
+    cfg = O.NetCfg()
+    params = O.synth_params(cfg, seed=1)
+    net = build_net(cfg, params, DEV)
+    with quiet():
+        mel = AugmentMelSTFT(fmin_aug_range=10, fmax_aug_range=2000).to(DEV)
+    model = PasstBasicWrapper(mel, net, mode="all").eval()
+    torch.manual_seed(2)
+    wave = 0.1 * torch.randn(2, 320000)
+    with torch.no_grad():
+        out = model(wave.to(DEV))
+    mcfg = O.MelCfg()
+    d = O.StepDraws(fmin=mcfg.fmin, fmax=mcfg.resolved_fmax())
+    with torch.no_grad():
+        m = O.mel_frontend(wave, mcfg, d, False).unsqueeze(1)
+        ref_logits, ref_feats = O.passt_forward(params, m, cfg, O.StepDraws())
+    assert relerr(out[:, :527], ref_logits) < 1e-2
+    assert relerr(out[:, 527:], ref_feats) < 1e-2
+
+
+def test_golden_fixture_logits():
+    """Candidate vs outputs of the *reference itself* (committed fixture, generated by tests/golden/make_golden.py)."""
+    O = _oracle()
+    path = os.path.join(os.path.dirname(__file__), "golden", "passt_golden.pt")
+    if not os.path.isfile(path):
+        pytest.skip("golden fixture missing")
+    G = torch.load(path)
+    cfg = O.NetCfg(**G["net_kw"])
+    params = O.synth_params(cfg, seed=G["param_seed"])
+    net = build_net(cfg, params, DEV)
+    torch.manual_seed(G["input_seed"])
+    x = torch.randn(*G["x_shape"])
+    net.train(True)
+    torch.manual_seed(G["rng_seed"])
+    logits, feats = net(x.to(DEV))
+    plan = net.last_plan
+    assert torch.equal(plan.t_keep, G["t_keep"]) and torch.equal(plan.f_keep, G["f_keep"])
+    assert relerr(logits, G["train_logits"]) < 1e-2
+    net.eval()
+    with torch.no_grad():
+        logits, feats = net(x.to(DEV))
+    assert relerr(logits, G["eval_logits"]) < 1e-2
+    assert relerr(feats, G["eval_features"]) < 1e-2
