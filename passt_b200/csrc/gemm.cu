@@ -6,7 +6,8 @@
 // One persistent, warp-specialised kernel:
 //   warp 0      : TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
-//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store / reduce-add)
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store / reduce-add);
+//                 two warps per TMEM lane quadrant, each owning half of the tile's N columns
 // Accumulators are double-buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
 //
@@ -81,16 +82,17 @@ int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
 // ---------------------------------------------------------------------------------------------
 enum GemmMode : int {
   kBiasBf16 = 0,      // C = bf16(acc + bias)
-  kBiasGeluBf16 = 1,  // C = bf16(acc + bias), C2 = bf16(gelu(acc + bias))
+  kBiasGeluBf16 = 1,  // C = bf16(gelu'(acc + bias)), C2 = bf16(gelu(acc + bias))
   kRowTabF32 = 2,     // C = fp32(acc + tab[row % period, col])
-  kGeluGradBf16 = 3,  // C = bf16(acc * gelu'(aux[row, col]))
+  kGeluGradBf16 = 3,  // C = bf16(acc * aux[row, col])   (aux = gelu'(pre) saved by mode 1)
   kWgradF32 = 4,      // C += fp32(acc)   (MN-major operands, split-K, TMA reduce-add)
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant, each owning half of the N columns
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct GemmParams {
   int M, N, K;             // D is [M,N]; K = contraction length
@@ -98,7 +100,7 @@ struct GemmParams {
   int k_blocks;            // total BK blocks along K
   int splits;              // split-K factor (1 for TN modes)
   const float* bias;       // [N] or nullptr
-  const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 pre[M, ld_aux]
+  const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 gelu'(pre) [M, ld_aux]
   int aux_period;          // mode 2
   int ld_aux;              // elements
   // UMMA smem-descriptor strides; exposed so the bring-up test can probe alternatives without a rebuild
@@ -113,13 +115,39 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBufBytes = 32 * 128;               // 32 rows x 128 B
-  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;      // 4 warps x 2 buffers
+  static constexpr int kEpiBufBytes = 32 * 64;                       // 32 rows x 64 B (SWIZZLE_64B boxes)
+  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;     // 2 buffers per epilogue warp
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + align slack
-  static constexpr int kColsPerChunk = kOutF32 ? 32 : 64;    // one 128-byte output row segment
+  static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;           // one 64-byte output row segment
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact-erf GELU and its derivative from one rcp + one ex2 (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7):
+//   gelu(x) = x * Phi(x),  gelu'(x) = Phi(x) + x * phi(x),  Phi = 0.5 (1 + erf(x / sqrt 2)),  phi = e^{-x^2/2}/sqrt(2 pi)
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float u = x * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, fabsf(u), 1.0f));
+  const float e = fast_ex2(u * u * -1.4426950408889634f);            // exp(-u^2) = exp(-x^2/2)
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float erf_abs = fmaf(-q * t, e, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, u), 0.5f);
+  g = x * cdf;
+  dg = fmaf(x * e, 0.3989422804014327f, cdf);
+}
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -150,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -233,8 +261,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may touch
-    uint8_t* my_epi = epi_smem + (warp - 2) * 2 * Cfg::kEpiBufBytes;
+    const int ew = warp - 2;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;          // which half of the BN columns this warp owns
+    uint8_t* my_epi = epi_smem + ew * 2 * Cfg::kEpiBufBytes;
+    const uint32_t swz = uint32_t((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the address
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
@@ -249,20 +280,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += Cfg::kColsPerChunk) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += Cfg::kColsPerChunk) {
         const int col0 = n_blk * BN + c0;
         if (!Cfg::kOutF32) {
-          uint32_t ra[32], rb[32];
+          uint32_t ra[32];
           tmem_ld_x32(taddr + c0, ra);
-          tmem_ld_x32(taddr + c0 + 32, rb);
           tmem_ld_wait();
-          float v[64];
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(ra[i]); v[32 + i] = __uint_as_float(rb[i]); }
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
           if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
             if (p.bias) {
 #pragma unroll
-              for (int i = 0; i < 64; i += 4) {
+              for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
@@ -273,30 +303,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
                                                                size_t(row) * p.ld_aux + col0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < 4; ++i) {
                 const uint4 u = __ldg(ap + i);
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                  v[i * 8 + 2 * j] *= gelu_exact_grad(__low2float(h2));
-                  v[i * 8 + 2 * j + 1] *= gelu_exact_grad(__high2float(h2));
+                  v[i * 8 + 2 * j] *= __low2float(h2);
+                  v[i * 8 + 2 * j + 1] *= __high2float(h2);
                 }
               }
             }
           }
-          // staging buffer must have been fully read by the TMA store issued two chunks ago
+          float w2[32];
+          if (MODE == kBiasGeluBf16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float g, dg;
+              gelu_and_grad(v[i], g, dg);
+              v[i] = dg;     // C  <- gelu'(pre)  (what the backward epilogue multiplies by)
+              w2[i] = g;     // C2 <- gelu(pre)
+            }
+          }
+          // staging buffer must have been fully read by the TMA store issued two stores ago
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* sbuf = my_epi + buf * Cfg::kEpiBufBytes;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             uint4 o;
             o.x = pack_bf16(v[ch * 8 + 0], v[ch * 8 + 1]);
             o.y = pack_bf16(v[ch * 8 + 2], v[ch * 8 + 3]);
             o.z = pack_bf16(v[ch * 8 + 4], v[ch * 8 + 5]);
             o.w = pack_bf16(v[ch * 8 + 6], v[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
           }
           fence_proxy_async();
           __syncwarp();
@@ -310,13 +350,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             uint8_t* sbuf2 = my_epi + buf * Cfg::kEpiBufBytes;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = 0; ch < 4; ++ch) {
               uint4 o;
-              o.x = pack_bf16(gelu_exact(v[ch * 8 + 0]), gelu_exact(v[ch * 8 + 1]));
-              o.y = pack_bf16(gelu_exact(v[ch * 8 + 2]), gelu_exact(v[ch * 8 + 3]));
-              o.z = pack_bf16(gelu_exact(v[ch * 8 + 4]), gelu_exact(v[ch * 8 + 5]));
-              o.w = pack_bf16(gelu_exact(v[ch * 8 + 6]), gelu_exact(v[ch * 8 + 7]));
-              *reinterpret_cast<uint4*>(sbuf2 + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
+              o.x = pack_bf16(w2[ch * 8 + 0], w2[ch * 8 + 1]);
+              o.y = pack_bf16(w2[ch * 8 + 2], w2[ch * 8 + 3]);
+              o.z = pack_bf16(w2[ch * 8 + 4], w2[ch * 8 + 5]);
+              o.w = pack_bf16(w2[ch * 8 + 6], w2[ch * 8 + 7]);
+              *reinterpret_cast<uint4*>(sbuf2 + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
             }
             fence_proxy_async();
             __syncwarp();
@@ -327,18 +367,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             buf ^= 1;
           }
         } else {
-          uint32_t ra[32];
-          tmem_ld_x32(taddr + c0, ra);
+          uint32_t ra[16];
+          tmem_ld_x16(taddr + c0, ra);
           tmem_ld_wait();
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
           if (MODE == kRowTabF32) {
             if (row < p.M) {
               const float4* tp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
                                                                  size_t(row % p.aux_period) * p.ld_aux + col0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < 4; ++i) {
                 const float4 t4 = __ldg(tp + i);
                 v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
               }
@@ -348,9 +388,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           uint8_t* sbuf = my_epi + buf * Cfg::kEpiBufBytes;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             float4 o = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-            *reinterpret_cast<float4*>(sbuf + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
+            *reinterpret_cast<float4*>(sbuf + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
           }
           fence_proxy_async();
           __syncwarp();
@@ -413,17 +453,17 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
       return rc;
   }
   if (Cfg::kOutF32) {
-    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, uint64_t(ldc) * 4, 32, 32,
-                           CU_TENSOR_MAP_SWIZZLE_128B)))
+    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, uint64_t(ldc) * 4, 32, 16,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
     tmC2 = tmC;
   } else {
-    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 64,
-                           CU_TENSOR_MAP_SWIZZLE_128B)))
+    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
     if (MODE == kBiasGeluBf16) {
-      if ((rc = make_tmap_2d(&tmC2, C2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 64,
-                             CU_TENSOR_MAP_SWIZZLE_128B)))
+      if ((rc = make_tmap_2d(&tmC2, C2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
+                             CU_TENSOR_MAP_SWIZZLE_64B)))
         return rc;
     } else {
       tmC2 = tmC;

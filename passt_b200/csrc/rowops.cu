@@ -78,24 +78,22 @@ ln_fwd_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ 
 // LayerNorm backward (+ fused residual-gradient add, bf16 copy, d_gamma/d_beta/colsum partials)
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnBwdWarps = 8;
-__global__ void __launch_bounds__(kLnBwdWarps * 32)
+constexpr int kLnBwdSmem = kLnBwdWarps * 3 * D * 4;   // per-warp private column accumulators (d_gamma, d_beta, colsum)
+// Column accumulators live in shared memory (private per warp, float4 read-modify-write, no atomics) instead of 72
+// registers per thread: the kernel is HBM-bound and needs the occupancy more than it needs the registers.
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* g_in,
               float* g_out, __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ colsum, int M, int rows_per_cta) {
-  __shared__ float red[kLnBwdWarps][D];
+  extern __shared__ float4 ln_acc4[];
+  float* acc_all = reinterpret_cast<float*>(ln_acc4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* acc = acc_all + warp * 3 * D;      // [3][D]
+  for (int i = lane; i < 3 * D / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(M, r0 + rows_per_cta);
-  float acc_g[kVec * 4], acc_b[kVec * 4], acc_c[kVec * 4];
-#pragma unroll
-  for (int i = 0; i < kVec * 4; ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; acc_c[i] = 0.f; }
-  float gam[kVec * 4];
-#pragma unroll
-  for (int i = 0; i < kVec; ++i) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4));
-    gam[4 * i] = g.x; gam[4 * i + 1] = g.y; gam[4 * i + 2] = g.z; gam[4 * i + 3] = g.w;
-  }
   for (int r = r0 + warp; r < r1; r += kLnBwdWarps) {
     const size_t off = size_t(r) * D;
     const float mu = mean[r], rs = rstd[r];
@@ -106,20 +104,24 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
       const int c = i * 128 + lane * 4;
       const float4 xv = *reinterpret_cast<const float4*>(x + off + c);
       const uint2 d = *reinterpret_cast<const uint2*>(dh + off + c);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const __nv_bfloat162 d0 = *reinterpret_cast<const __nv_bfloat162*>(&d.x);
       const __nv_bfloat162 d1 = *reinterpret_cast<const __nv_bfloat162*>(&d.y);
       xh[4 * i] = (xv.x - mu) * rs; xh[4 * i + 1] = (xv.y - mu) * rs;
       xh[4 * i + 2] = (xv.z - mu) * rs; xh[4 * i + 3] = (xv.w - mu) * rs;
       dy[4 * i] = __low2float(d0); dy[4 * i + 1] = __high2float(d0);
       dy[4 * i + 2] = __low2float(d1); dy[4 * i + 3] = __high2float(d1);
+      float4* a_g = reinterpret_cast<float4*>(acc + c);
+      float4* a_b = reinterpret_cast<float4*>(acc + D + c);
+      float4 ag = *a_g, ab = *a_b;
+      ag.x += dy[4 * i] * xh[4 * i]; ag.y += dy[4 * i + 1] * xh[4 * i + 1];
+      ag.z += dy[4 * i + 2] * xh[4 * i + 2]; ag.w += dy[4 * i + 3] * xh[4 * i + 3];
+      ab.x += dy[4 * i]; ab.y += dy[4 * i + 1]; ab.z += dy[4 * i + 2]; ab.w += dy[4 * i + 3];
+      *a_g = ag; *a_b = ab;
+      // from here on dy holds dy * gamma
+      dy[4 * i] *= g.x; dy[4 * i + 1] *= g.y; dy[4 * i + 2] *= g.z; dy[4 * i + 3] *= g.w;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc_g[4 * i + e] += dy[4 * i + e] * xh[4 * i + e];
-        acc_b[4 * i + e] += dy[4 * i + e];
-        const float dg = dy[4 * i + e] * gam[4 * i + e];
-        sa += dg * xh[4 * i + e];
-        sb += dg;
-      }
+      for (int e = 0; e < 4; ++e) { sa += dy[4 * i + e] * xh[4 * i + e]; sb += dy[4 * i + e]; }
     }
     sa = warp_sum(sa) * (1.0f / D);
     sb = warp_sum(sb) * (1.0f / D);
@@ -128,12 +130,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
       const int c = i * 128 + lane * 4;
       float o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = rs * (dy[4 * i + e] * gam[4 * i + e] - sb - xh[4 * i + e] * sa);
+      for (int e = 0; e < 4; ++e) o[e] = rs * (dy[4 * i + e] - sb - xh[4 * i + e] * sa);
       if (g_in) {
         const float4 gi = *reinterpret_cast<const float4*>(g_in + off + c);
         o[0] += gi.x; o[1] += gi.y; o[2] += gi.z; o[3] += gi.w;
       }
       if (g_out) *reinterpret_cast<float4*>(g_out + off + c) = make_float4(o[0], o[1], o[2], o[3]);
+      float4* a_c = reinterpret_cast<float4*>(acc + 2 * D + c);
+      float4 ac = *a_c;
       if (g_out_bf16) {
         uint2 ob;
         ob.x = pack_bf16(o[0], o[1]);
@@ -142,32 +146,23 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
         // bias gradients are taken from the bf16 values the wgrad GEMM will also see
         const __nv_bfloat162 q0 = *reinterpret_cast<const __nv_bfloat162*>(&ob.x);
         const __nv_bfloat162 q1 = *reinterpret_cast<const __nv_bfloat162*>(&ob.y);
-        acc_c[4 * i] += __low2float(q0); acc_c[4 * i + 1] += __high2float(q0);
-        acc_c[4 * i + 2] += __low2float(q1); acc_c[4 * i + 3] += __high2float(q1);
+        ac.x += __low2float(q0); ac.y += __high2float(q0); ac.z += __low2float(q1); ac.w += __high2float(q1);
       } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc_c[4 * i + e] += o[e];
+        ac.x += o[0]; ac.y += o[1]; ac.z += o[2]; ac.w += o[3];
       }
+      *a_c = ac;
     }
   }
-  // cross-warp reduction of the three column accumulators, then one atomic per column per CTA
+  __syncthreads();
+  // cross-warp reduction, then one atomic per column per CTA
   float* outs[3] = {dgamma, dbeta, colsum};
 #pragma unroll
   for (int which = 0; which < 3; ++which) {
     if (outs[which] == nullptr) continue;  // uniform
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kVec; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float val = which == 0 ? acc_g[4 * i + e] : (which == 1 ? acc_b[4 * i + e] : acc_c[4 * i + e]);
-        red[warp][i * 128 + lane * 4 + e] = val;
-      }
-    __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < kLnBwdWarps; ++w) s += red[w][c];
+      for (int w = 0; w < kLnBwdWarps; ++w) s += acc_all[w * 3 * D + which * D + c];
       atomicAdd(outs[which] + c, s);
     }
   }
@@ -536,7 +531,12 @@ int passt_ln_bwd(const void* dh_bf16, const float* x, const float* mean, const f
   int rows_per_cta = (M + ctas - 1) / ctas;
   if (rows_per_cta < kLnBwdWarps) rows_per_cta = kLnBwdWarps;
   ctas = (M + rows_per_cta - 1) / rows_per_cta;
-  ln_bwd_kernel<<<ctas, kLnBwdWarps * 32, 0, (cudaStream_t)stream>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
+    attr_set = true;
+  }
+  ln_bwd_kernel<<<ctas, kLnBwdWarps * 32, kLnBwdSmem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dh_bf16, x, mean, rstd, gamma, g_in, g_out, (__nv_bfloat16*)g_out_bf16, dgamma, dbeta,
       colsum, M, rows_per_cta);
   PB_LAUNCH_CHECK();
