@@ -38,6 +38,8 @@ int passt_mel_forward(const void* workspace, const float* wave, float* out, int 
 int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                     int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,
                     int max_ctas, void* stream);
+/* 1 (default): 2-CTA tcgen05 (cta_group::2, 256x256 cluster tiles) where the shape allows; 0: 1-CTA kernel only */
+void passt_gemm_set_2cta(int enable);
 /* bring-up hook: override the UMMA shared-memory descriptor strides (6 uint32); active=0 restores defaults */
 void passt_gemm_debug_desc(int active, const unsigned* v6);
 

@@ -19,6 +19,7 @@ vp, i32, f32, f64 = C.c_void_p, C.c_int, C.c_float, C.c_double
 
 _SIGS = {
     "passt_gemm_debug_desc": (None, [i32, vp]),
+    "passt_gemm_set_2cta": (None, [i32]),
     "passt_gemm_bf16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "passt_mel_workspace_bytes": (C.c_size_t, []),
     "passt_mel_init": (i32, [vp, i32, vp]),
@@ -95,7 +96,7 @@ def check(rc: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
+_LAUNCHES = {"passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
              "passt_attn_bwd_workspace_bytes": 0}
 _launch_counter = 0
 

@@ -5,12 +5,16 @@
 //
 // One CTA owns one (128-key tile, head, clip) and loops over the query tiles.  Everything is computed in the
 // transposed (keys x queries) frame so that the tiles TMA brings in are used as-is by every MMA:
-//     S^T  = K  Q^T        (A = K  K-major,            B = Q  K-major)        -> TMEM [0,128)
-//     dP^T = V  dO^T       (A = V  K-major,            B = dO K-major)        -> TMEM [128,256)
+//     S^T  = K  Q^T        (A = K  in TMEM,            B = Q  K-major)        -> TMEM [0,128)
+//     dP^T = V  dO^T       (A = V  in TMEM,            B = dO K-major)        -> TMEM [128,256)
 //     P^T  = exp2(S^T c - lse[q]),  dS^T = P^T (dP^T - D[q])      (8 compute warps, thread = key row)
-//     dV  += P^T  dO       (A = P^T  K-major (smem),   B = dO MN-major: same bytes as above)  -> TMEM [256,320)
-//     dK  += dS^T Q        (A = dS^T K-major (smem),   B = Q  MN-major)                        -> TMEM [320,384)
-//     dQ_i = dS   K        (A = dS^T read MN-major,    B = K  MN-major)                        -> TMEM [384,448)
+//     dV  += P^T  dO       (A = P^T  in TMEM,          B = dO MN-major: same smem bytes as above) -> TMEM [256,320)
+//     dK  += dS^T Q        (A = dS^T in TMEM,          B = Q  MN-major)                           -> TMEM [320,384)
+//     dQ_i = dS   K        (A = dS^T smem MN-major,    B = K  MN-major)                           -> TMEM [384,448)
+// M=128 x N<=128 MMAs are operand-bandwidth bound when A is read from shared memory, so every A operand that can
+// live in tensor memory does: K and V are copied there once per CTA (columns [448,512)), P^T / dS^T are written by
+// the compute warps with tcgen05.st over the S^T / dP^T columns they have just consumed (bf16 pairs, half the
+// width).  Only dQ keeps a shared-memory A operand (it needs dS with queries on the M axis).
 // dQ_i tiles from different key tiles are summed in an fp32 buffer with TMA reduce-add; a small kernel then
 // scales and packs dQ into the dqkv tensor.  D = rowsum(dO * O) comes from a pre-pass.
 #include "common.cuh"
@@ -23,60 +27,63 @@ constexpr int kTile = 128;
 
 struct AttnBwdParams {
   int N, H;
+  int n_kvt;         // key tiles per (clip, head)
+  int total_items;   // B * H * n_kvt
   float scale_log2, scale;
   const float* lse;   // [B,H,N]
   const float* Dsum;  // [B,H,N]
 };
 
 struct AttnBwdSmem {
-  static constexpr int kK = 0;
-  static constexpr int kV = kK + 16384;
-  static constexpr int kQdO = kV + 16384;            // 2 stages x (Q 16 KB + dO 16 KB)
-  static constexpr int kPT = kQdO + 2 * 32768;       // 32 KB
-  static constexpr int kdST = kPT + 32768;           // 32 KB
-  static constexpr int kdQ = kdST + 32768;           // 32 KB fp32 staging
+  static constexpr int kKV = 0;                      // 2 item buffers x (K 16 KB + V 16 KB)
+  static constexpr int kQdO = kKV + 2 * 32768;       // 2 stages x (Q 16 KB + dO 16 KB)
+  static constexpr int kdST = kQdO + 2 * 32768;      // 32 KB  dS^T (bf16) for the dQ MMA
+  static constexpr int kdQ = kdST + 32768;           // 32 KB  fp32 dQ staging; dK/dV staging at item end
   static constexpr int kVec = kdQ + 32768;           // lse/D: 2 x 2 x 128 floats
   static constexpr int kBars = kVec + 2048;
-  static constexpr int kTotal = kBars + 128;
+  static constexpr int kTotal = kBars + 256;
 };
 
+// Persistent: each CTA walks a strided list of (key tile, head, clip) items; the TMA producer prefetches the next
+// item's K/V and Q/dO tiles while the current item is still being processed.
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQKV, const __grid_constant__ CUtensorMap tmdQacc,
                 const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sK = smem + AttnBwdSmem::kK;
-  uint8_t* sV = smem + AttnBwdSmem::kV;
+  uint8_t* sKV = smem + AttnBwdSmem::kKV;
   uint8_t* sQdO = smem + AttnBwdSmem::kQdO;
-  uint8_t* sPT = smem + AttnBwdSmem::kPT;
   uint8_t* sdST = smem + AttnBwdSmem::kdST;
   uint8_t* sdQ = smem + AttnBwdSmem::kdQ;
   float* sVec = reinterpret_cast<float*>(smem + AttnBwdSmem::kVec);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBars);
-  uint64_t* kv_full = bars;          // [1]
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;     // [1]
-  uint64_t* pds_full = bars + 6;     // [1] 256 arrivals
-  uint64_t* dq_full = bars + 7;      // [1]
-  uint64_t* dkv_full = bars + 8;     // [1]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2]  tcgen05.commit after the item's last MMA
+  uint64_t* qdo_full = bars + 4;     // [2]
+  uint64_t* qdo_empty = bars + 6;    // [2]
+  uint64_t* sdp_full = bars + 8;     // [1]
+  uint64_t* pds_full = bars + 9;     // [1] 256 arrivals
+  uint64_t* dq_full = bars + 10;     // [1]
+  uint64_t* dkv_full = bars + 11;    // [1]
+  uint64_t* kv_ready = bars + 12;    // [1] 256 arrivals: K, V copied into TMEM
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * kTile;
-  const int h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.N + kTile - 1) / kTile;
   const int C = p.H * kBHd;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQKV); tma_prefetch_desc(&tmdQacc);
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1);
+    }
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
     mbar_init(dkv_full, 1);
+    mbar_init(kv_ready, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_holder);
@@ -85,69 +92,79 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
-                 tdQ = tmem_base + 384;
+                 tdQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
+  // P^T (bf16 pairs) for query half hc lives at tS + 64*hc .. +32, dS^T at tdP + 64*hc .. +32: each compute warp
+  // only overwrites score columns it has itself already read
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * 16384);
-      tma_load_3d(sK, &tmQKV, kv_full, C + h * kBHd, kv0, b);
-      tma_load_3d(sV, &tmQKV, kv_full, 2 * C + h * kBHd, kv0, b);
-      for (int i = 0; i < n_q; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * 16384);
-        tma_load_3d(sQdO + s * 32768, &tmQKV, &qdo_full[s], h * kBHd, i * kTile, b);
-        tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, &qdo_full[s], h * kBHd, i * kTile, b);
+      uint32_t g = 0, n = 0;
+      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+        const int kvt = it % p.n_kvt, h = (it / p.n_kvt) % p.H, b = it / (p.n_kvt * p.H);
+        const uint32_t kb = n & 1;
+        mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * 16384);
+        tma_load_3d(sKV + kb * 32768, &tmQKV, &kv_full[kb], C + h * kBHd, kvt * kTile, b);
+        tma_load_3d(sKV + kb * 32768 + 16384, &tmQKV, &kv_full[kb], 2 * C + h * kBHd, kvt * kTile, b);
+        for (int i = 0; i < n_q; ++i, ++g) {
+          const uint32_t s = g & 1;
+          mbar_wait(&qdo_empty[s], ((g >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&qdo_full[s], 2 * 16384);
+          tma_load_3d(sQdO + s * 32768, &tmQKV, &qdo_full[s], h * kBHd, i * kTile, b);
+          tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, &qdo_full[s], h * kBHd, i * kTile, b);
+        }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t id_q = make_idesc_bf16(128, 64, 1, 1);
-    mbar_wait(kv_full, 0);
-    for (int i = 0; i < n_q; ++i) {
-      const int s = i & 1;
-      mbar_wait(&qdo_full[s], (i >> 1) & 1);
+    uint32_t g = 0, n = 0;
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+      const uint32_t kb = n & 1;
+      mbar_wait(kv_ready, n & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      const uint32_t aQ = smem_u32(sQdO + s * 32768), adO = aQ + 16384;
-      const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
-      if (lane == 0) {
+      const uint32_t aK = smem_u32(sKV + kb * 32768);
+      const uint32_t adST = smem_u32(sdST);
+      for (int i = 0; i < n_q; ++i, ++g) {
+        const uint32_t s = g & 1;
+        mbar_wait(&qdo_full[s], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQdO + s * 32768), adO = aQ + 16384;
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tS, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024),
-                       id_s, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tS, tK + k * 8, make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tdP, make_smem_desc_sw128(aV + k * 32, 16, 1024),
-                       make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k > 0);
-        tc_commit(sdp_full);
-      }
-      __syncwarp();
-      mbar_wait(pds_full, i & 1);
-      tc_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * 32;   // K-major A, contraction = queries
-          umma_bf16_ss(tdV, make_smem_desc_sw128(aPT + a_off, 16, 1024),
-                       make_smem_desc_sw128(adO + k * 2048, 8192, 1024), id_kv, (i > 0 || k > 0));
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tdP, tV + k * 8, make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k > 0);
+          tc_commit(sdp_full);
         }
+        __syncwarp();
+        mbar_wait(pds_full, g & 1);
+        tc_fence_after();
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_bf16_ss(tdK, make_smem_desc_sw128(adST + a_off, 16, 1024),
-                       make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), id_kv, (i > 0 || k > 0));
+          for (int k = 0; k < 8; ++k)   // contraction = queries; 16 queries = 8 TMEM columns of packed bf16
+            umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(adO + k * 2048, 8192, 1024),
+                         id_kv, (i > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(aQ + k * 2048, 8192, 1024),
+                         id_kv, (i > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
+            umma_bf16_ss(tdQ, make_smem_desc_sw128(adST + k * 2048, 16384, 1024),
+                         make_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_q, k > 0);
+          tc_commit(dq_full);
+          tc_commit(&qdo_empty[s]);
+          if (i == n_q - 1) {
+            tc_commit(dkv_full);
+            tc_commit(&kv_empty[kb]);
+          }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
-          umma_bf16_ss(tdQ, make_smem_desc_sw128(adST + k * 2048, 16384, 1024),
-                       make_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_q, k > 0);
-        tc_commit(dq_full);
-        tc_commit(&qdo_empty[s]);
-        if (i == n_q - 1) tc_commit(dkv_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===================== compute warps =====================
@@ -158,108 +175,142 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int ct = threadIdx.x - 64;    // 0..255
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const float log2e = 1.4426950408889634f;
-    for (int i = 0; i < n_q; ++i) {
-      const int q0 = i * kTile;
-      float* s_lse = sVec + (i & 1) * 256;
-      float* s_D = s_lse + 128;
-      if (ct == 0) tma_store_wait_read<0>();   // dQ staging of the previous step has been read
-      if (ct < 128) {
-        const int qq = q0 + ct;
-        s_lse[ct] = qq < p.N ? p.lse[(size_t(b) * p.H + h) * p.N + qq] * log2e : INFINITY;
-      } else {
-        const int qq = q0 + ct - 128;
-        s_D[ct - 128] = qq < p.N ? p.Dsum[(size_t(b) * p.H + h) * p.N + qq] : 0.f;
+    // K (warps with hc == 0) and V (hc == 1) rows of item n: swizzled smem -> packed bf16 in TMEM
+    auto stage_kv = [&](uint32_t n) {
+      const uint32_t kb = n & 1;
+      mbar_wait(&kv_full[kb], (n >> 1) & 1);
+      const uint8_t* src = sKV + kb * 32768 + (hc == 0 ? 0 : 16384);
+      uint32_t kv[32];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + r * 128 + ((ch ^ (r & 7)) << 4));
+        kv[ch * 4] = u.x; kv[ch * 4 + 1] = u.y; kv[ch * 4 + 2] = u.z; kv[ch * 4 + 3] = u.w;
       }
-      named_bar_sync(1, 256);
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = hc * 64 + c * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_x32(tS + lane_addr + col0, sv);
-        tmem_ld_x32(tdP + lane_addr + col0, dv);
-        tmem_ld_wait();
-        float pt[32], ds[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float pe = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - s_lse[col0 + e]);
-          pt[e] = pe;
-          ds[e] = pe * (__uint_as_float(dv[e]) - s_D[col0 + e]);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = c * 4 + g;   // 16-byte chunk inside this 64-query half
-          const uint32_t off = hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4);
-          uint4 o;
-          o.x = pack_bf16(pt[g * 8 + 0], pt[g * 8 + 1]); o.y = pack_bf16(pt[g * 8 + 2], pt[g * 8 + 3]);
-          o.z = pack_bf16(pt[g * 8 + 4], pt[g * 8 + 5]); o.w = pack_bf16(pt[g * 8 + 6], pt[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(sPT + off) = o;
-          o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-          o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(sdST + off) = o;
-        }
-      }
+      tmem_st_x32((hc == 0 ? tK : tV) + lane_addr, kv);
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(pds_full);
-      // ---- drain dQ_i (rows = queries) -> fp32 staging -> TMA reduce-add into the accumulation buffer
-      mbar_wait(dq_full, i & 1);
+      mbar_arrive(kv_ready);
+    };
+    uint32_t g = 0, n = 0;
+    if (blockIdx.x < p.total_items) stage_kv(0);
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+      const int kvt = it % p.n_kvt, h = (it / p.n_kvt) % p.H, b = it / (p.n_kvt * p.H);
+      const int kv0 = kvt * kTile;
+      const bool has_next = (it + int(gridDim.x) < p.total_items);
+      for (int i = 0; i < n_q; ++i, ++g) {
+        const int q0 = i * kTile;
+        float* s_lse = sVec + (g & 1) * 256;
+        float* s_D = s_lse + 128;
+        if (ct == 0) tma_store_wait_read<0>();   // staging (dQ of the previous step / dK,dV of the previous item) was read
+        if (ct < 128) {
+          const int qq = q0 + ct;
+          s_lse[ct] = qq < p.N ? p.lse[(size_t(b) * p.H + h) * p.N + qq] * log2e : INFINITY;
+        } else {
+          const int qq = q0 + ct - 128;
+          s_D[ct - 128] = qq < p.N ? p.Dsum[(size_t(b) * p.H + h) * p.N + qq] : 0.f;
+        }
+        named_bar_sync(1, 256);
+        mbar_wait(sdp_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = hc * 64 + c * 32;
+          uint32_t sv[32], dv[32];
+          tmem_ld_x32(tS + lane_addr + col0, sv);
+          tmem_ld_x32(tdP + lane_addr + col0, dv);
+          tmem_ld_wait();
+          uint32_t pp[16], dd2[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(s_lse + col0 + e);
+            const float4 d4 = *reinterpret_cast<const float4*>(s_D + col0 + e);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, -l4.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -l4.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e + 2]), p.scale_log2, -l4.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e + 3]), p.scale_log2, -l4.w));
+            pp[e >> 1] = pack_bf16(p0, p1);
+            pp[(e >> 1) + 1] = pack_bf16(p2, p3);
+            dd2[e >> 1] = pack_bf16(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
+            dd2[(e >> 1) + 1] =
+                pack_bf16(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
+          }
+          tmem_st_x16(tS + lane_addr + hc * 64 + c * 16, pp);     // A operand of dV += P^T dO
+          tmem_st_x16(tdP + lane_addr + hc * 64 + c * 16, dd2);   // A operand of dK += dS^T Q
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {   // dS^T also goes to smem: dQ = dS K reads it MN-major
+            const int ch = c * 4 + gq;       // 16-byte chunk inside this 64-query half
+            const uint32_t off = hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(sdST + off) =
+                make_uint4(dd2[gq * 4], dd2[gq * 4 + 1], dd2[gq * 4 + 2], dd2[gq * 4 + 3]);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(pds_full);
+        // all S^T / dP^T MMAs of this item are complete after its last sdp_full: K/V columns are free -> stage the
+        // next item's K/V now so its first MMAs overlap this item's tail
+        if (i == n_q - 1 && has_next) stage_kv(n + 1);
+        // ---- drain dQ_i (rows = queries) -> fp32 staging -> TMA reduce-add into the accumulation buffer
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          tmem_ld_x32(tdQ + lane_addr + hc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float4 o = make_float4(__uint_as_float(v[ch * 4]), __uint_as_float(v[ch * 4 + 1]),
+                                   __uint_as_float(v[ch * 4 + 2]), __uint_as_float(v[ch * 4 + 3]));
+            *reinterpret_cast<float4*>(sdQ + hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = o;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (ct == 0) {
+          tma_reduce_add_3d(&tmdQacc, sdQ, h * kBHd, q0, b);
+          tma_reduce_add_3d(&tmdQacc, sdQ + 16384, h * kBHd + 32, q0, b);
+          tma_store_commit();
+        }
+      }
+      // ---- item epilogue: dK (scaled), dV -> bf16 -> staging (dQ staging buffer) -> TMA store
+      mbar_wait(dkv_full, n & 1);
       tc_fence_after();
+      if (ct == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, 256);
       {
-        uint32_t v[32];
-        tmem_ld_x32(tdQ + lane_addr + hc * 32, v);
+        uint32_t vv[32], kk[32];
+        tmem_ld_x32(tdV + lane_addr + hc * 32, vv);
+        tmem_ld_x32(tdK + lane_addr + hc * 32, kk);
         tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float4 o = make_float4(__uint_as_float(v[ch * 4]), __uint_as_float(v[ch * 4 + 1]),
-                                 __uint_as_float(v[ch * 4 + 2]), __uint_as_float(v[ch * 4 + 3]));
-          *reinterpret_cast<float4*>(sdQ + hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = o;
+        for (int gq = 0; gq < 4; ++gq) {
+          const int ch = hc * 4 + gq;
+          const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(vv[gq * 8 + 0]), __uint_as_float(vv[gq * 8 + 1]));
+          o.y = pack_bf16(__uint_as_float(vv[gq * 8 + 2]), __uint_as_float(vv[gq * 8 + 3]));
+          o.z = pack_bf16(__uint_as_float(vv[gq * 8 + 4]), __uint_as_float(vv[gq * 8 + 5]));
+          o.w = pack_bf16(__uint_as_float(vv[gq * 8 + 6]), __uint_as_float(vv[gq * 8 + 7]));
+          *reinterpret_cast<uint4*>(sdQ + off) = o;                                  // dV tile
+          o.x = pack_bf16(__uint_as_float(kk[gq * 8 + 0]) * p.scale, __uint_as_float(kk[gq * 8 + 1]) * p.scale);
+          o.y = pack_bf16(__uint_as_float(kk[gq * 8 + 2]) * p.scale, __uint_as_float(kk[gq * 8 + 3]) * p.scale);
+          o.z = pack_bf16(__uint_as_float(kk[gq * 8 + 4]) * p.scale, __uint_as_float(kk[gq * 8 + 5]) * p.scale);
+          o.w = pack_bf16(__uint_as_float(kk[gq * 8 + 6]) * p.scale, __uint_as_float(kk[gq * 8 + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(sdQ + 16384 + off) = o;                          // dK tile
         }
       }
       tc_fence_before();
       fence_proxy_async();
       named_bar_sync(1, 256);
       if (ct == 0) {
-        tma_reduce_add_3d(&tmdQacc, sdQ, h * kBHd, q0, b);
-        tma_reduce_add_3d(&tmdQacc, sdQ + 16384, h * kBHd + 32, q0, b);
+        tma_store_3d(&tmdQKV, sdQ + 16384, C + h * kBHd, kv0, b);   // dK
+        tma_store_3d(&tmdQKV, sdQ, 2 * C + h * kBHd, kv0, b);       // dV
         tma_store_commit();
       }
     }
-    // ---- epilogue: dK (scaled), dV -> bf16 -> staging (P^T / dS^T buffers are free) -> TMA store
-    mbar_wait(dkv_full, 0);
-    tc_fence_after();
-    {
-      uint32_t vv[32], kk[32];
-      tmem_ld_x32(tdV + lane_addr + hc * 32, vv);
-      tmem_ld_x32(tdK + lane_addr + hc * 32, kk);
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int ch = hc * 4 + g;
-        const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
-        uint4 o;
-        o.x = pack_bf16(__uint_as_float(vv[g * 8 + 0]), __uint_as_float(vv[g * 8 + 1]));
-        o.y = pack_bf16(__uint_as_float(vv[g * 8 + 2]), __uint_as_float(vv[g * 8 + 3]));
-        o.z = pack_bf16(__uint_as_float(vv[g * 8 + 4]), __uint_as_float(vv[g * 8 + 5]));
-        o.w = pack_bf16(__uint_as_float(vv[g * 8 + 6]), __uint_as_float(vv[g * 8 + 7]));
-        *reinterpret_cast<uint4*>(sPT + off) = o;
-        o.x = pack_bf16(__uint_as_float(kk[g * 8 + 0]) * p.scale, __uint_as_float(kk[g * 8 + 1]) * p.scale);
-        o.y = pack_bf16(__uint_as_float(kk[g * 8 + 2]) * p.scale, __uint_as_float(kk[g * 8 + 3]) * p.scale);
-        o.z = pack_bf16(__uint_as_float(kk[g * 8 + 4]) * p.scale, __uint_as_float(kk[g * 8 + 5]) * p.scale);
-        o.w = pack_bf16(__uint_as_float(kk[g * 8 + 6]) * p.scale, __uint_as_float(kk[g * 8 + 7]) * p.scale);
-        *reinterpret_cast<uint4*>(sdST + off) = o;
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    named_bar_sync(1, 256);
-    if (ct == 0) {
-      tma_store_3d(&tmdQKV, sdST, C + h * kBHd, kv0, b);       // dK
-      tma_store_3d(&tmdQKV, sPT, 2 * C + h * kBHd, kv0, b);    // dV
-      tma_store_commit();
-      tma_store_wait<0>();
-    }
+    if (ct == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -351,13 +402,15 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
     return rc;
   AttnBwdParams p;
   p.N = N; p.H = H; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.lse = lse; p.Dsum = Dsum;
+  p.n_kvt = (N + kTile - 1) / kTile;
+  p.total_items = B * H * p.n_kvt;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      AttnBwdSmem::kTotal));
     attr_set = true;
   }
-  dim3 grid((N + kTile - 1) / kTile, H, B);
+  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
   attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tmQKV, tmdO, tmdQKV, tmdQacc, p);
   PB_LAUNCH_CHECK();
   {

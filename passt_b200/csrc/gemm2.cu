@@ -1,0 +1,468 @@
+// passt_b200 — 2-CTA (tcgen05 cta_group::2) variant of the GEMM family (sm_100a only).
+//
+// Same math, operand layouts and epilogues as gemm.cu, but a cluster of two CTAs (one TPC) cooperates on a
+// 256 (M) x 256 (N) tile: each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows),
+// the leader CTA issues tcgen05.mma.cta_group::2 (M=256), and each CTA's tensor core writes its own 128 rows of D
+// into its own TMEM.  Per CTA the shared-memory traffic per k-block drops from 48 KB in + 48 KB out (1-CTA kernel:
+// measured 68 % tensor-pipe, shared-memory-bandwidth bound) to 32 KB in + 32 KB out.
+//
+// Barrier protocol (all barriers live at the same smem offset in both CTAs):
+//   full[s]   : leader's copy only is used.  count 1 (leader's expect_tx); BOTH CTAs' TMA loads complete_tx on it
+//               (cp.async.bulk.tensor .cta_group::2 with the peer bit of the barrier address cleared).
+//   empty[s]  : per CTA, count 1; tcgen05.commit ... multicast::cluster arrives on both CTAs' copies.
+//   tfull[a]  : per CTA, count 1; multicast commit after the last k-block of a tile.
+//   tempty[a] : leader's copy only, count 2*kEpiWarps; epilogue warps of both CTAs arrive (remote for rank 1).
+#include "gemm_defs.cuh"
+#include <cstdio>
+
+namespace pb {
+
+constexpr int kStages2 = 6;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same object in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_holder) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+template <int MODE>
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr bool kWgrad = (MODE == kWgradF32);
+  static constexpr bool kOutF32 = (MODE == kRowTabF32 || MODE == kWgradF32);
+  static constexpr int kABytes = BM * BK * 2;           // this CTA's 128 A rows
+  static constexpr int kBBytes = (BN / 2) * BK * 2;     // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBufBytes = 32 * 64;
+  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 1024;
+  static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;
+  static constexpr uint32_t kTmemCols = 2 * BN;
+};
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
+  using Cfg = Gemm2Cfg<MODE>;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  // both CTAs see the same dynamic-smem base offset, so the aligned offset is identical in the pair
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + kStages2 * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;                  // [kStages2]
+  uint64_t* empty_bar = bars + kStages2;      // [kStages2]
+  uint64_t* tfull_bar = bars + 2 * kStages2;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (MODE == kBiasGeluBf16) tma_prefetch_desc(&tmC2);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_holder);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // work items are 256x256 cluster tiles
+  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;    // m_tiles counts 256-row blocks here
+  const int kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int split = t / (p.m_tiles * p.n_tiles);
+        const int tt = t - split * (p.m_tiles * p.n_tiles);
+        const int m_blk = tt / p.n_tiles, n_blk = tt - m_blk * p.n_tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const int m0 = m_blk * 256 + int(rank) * BM;          // this CTA's A rows
+        const int n0 = n_blk * BN + int(rank) * (BN / 2);     // this CTA's half of B
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // bytes of both CTAs
+          if (!Cfg::kWgrad) {
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g)
+              tma_load_2d_2sm(sa + g * 8192, &tmA, &full_bar[stage], m0 + g * 64, kb * BK);
+#pragma unroll
+            for (int g = 0; g < (BN / 2) / 64; ++g)
+              tma_load_2d_2sm(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, kb * BK);
+          }
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, Cfg::kWgrad ? 1 : 0, Cfg::kWgrad ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int split = t / (p.m_tiles * p.n_tiles);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = make_smem_desc_sw128(sa + k * p.kstep_a, p.lbo_a, p.sbo_a);
+              const uint64_t db = make_smem_desc_sw128(sb + k * p.kstep_b, p.lbo_b, p.sbo_b);
+              umma_bf16_ss_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_2cta_mc(&empty_bar[stage]);
+            if (kb == kb1 - 1) tc_commit_2cta_mc(&tfull_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0 && lane == 0) tc_commit_2cta_mc(&tfull_bar[as]);
+        __syncwarp();
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs; each drains its own 128 rows) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* my_epi = epi_smem + ew * 2 * Cfg::kEpiBufBytes;
+    const uint32_t swz = uint32_t((lane >> 1) & 3);
+    int as = 0;
+    uint32_t aphase = 0;
+    int buf = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int split = t / (p.m_tiles * p.n_tiles);
+      const int tt = t - split * (p.m_tiles * p.n_tiles);
+      const int m_blk = tt / p.n_tiles, n_blk = tt - m_blk * p.n_tiles;
+      const int row0 = m_blk * 256 + int(rank) * BM + q * 32;
+      const int row = row0 + lane;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += Cfg::kColsPerChunk) {
+        const int col0 = n_blk * BN + c0;
+        if (!Cfg::kOutF32) {
+          uint32_t ra[32];
+          tmem_ld_x32(taddr + c0, ra);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+          if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
+          }
+          if (MODE == kGeluGradBf16) {
+            if (row < p.M) {
+              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                               size_t(row) * p.ld_aux + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(ap + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                  v[i * 8 + 2 * j] *= __low2float(h2);
+                  v[i * 8 + 2 * j + 1] *= __high2float(h2);
+                }
+              }
+            }
+          }
+          float w2[32];
+          if (MODE == kBiasGeluBf16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float g, dg;
+              gelu_and_grad(v[i], g, dg);
+              v[i] = dg;
+              w2[i] = g;
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sbuf = my_epi + buf * Cfg::kEpiBufBytes;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 o;
+            o.x = pack_bf16(v[ch * 8 + 0], v[ch * 8 + 1]);
+            o.y = pack_bf16(v[ch * 8 + 2], v[ch * 8 + 3]);
+            o.z = pack_bf16(v[ch * 8 + 4], v[ch * 8 + 5]);
+            o.w = pack_bf16(v[ch * 8 + 6], v[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sbuf, col0, row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+          if (MODE == kBiasGeluBf16) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            uint8_t* sbuf2 = my_epi + buf * Cfg::kEpiBufBytes;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint4 o;
+              o.x = pack_bf16(w2[ch * 8 + 0], w2[ch * 8 + 1]);
+              o.y = pack_bf16(w2[ch * 8 + 2], w2[ch * 8 + 3]);
+              o.z = pack_bf16(w2[ch * 8 + 4], w2[ch * 8 + 5]);
+              o.w = pack_bf16(w2[ch * 8 + 6], w2[ch * 8 + 7]);
+              *reinterpret_cast<uint4*>(sbuf2 + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC2, sbuf2, col0, row0);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+        } else {
+          uint32_t ra[16];
+          tmem_ld_x16(taddr + c0, ra);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
+          if (MODE == kRowTabF32) {
+            if (row < p.M) {
+              const float4* tp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
+                                                                 size_t(row % p.aux_period) * p.ld_aux + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t4 = __ldg(tp + i);
+                v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+              }
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sbuf = my_epi + buf * Cfg::kEpiBufBytes;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float4 o = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+            *reinterpret_cast<float4*>(sbuf + lane * 64 + ((uint32_t(ch) ^ swz) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (MODE == kWgradF32) tma_reduce_add_2d(&tmC, sbuf, col0, row0);
+            else tma_store_2d(&tmC, sbuf, col0, row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();     // both CTAs finished using TMEM / each other's barriers
+  if (warp == 1) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int MODE>
+static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
+                          int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits,
+                          cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<MODE>;
+  constexpr int BN = Cfg::BN;
+  if (N % BN != 0 || (lda % 8) || (ldb % 8)) return PB_ERR_BAD_ARG;
+  CUtensorMap tmA, tmB, tmC, tmC2;
+  int rc;
+  if (!Cfg::kWgrad) {
+    if (K % 8) return PB_ERR_BAD_ARG;
+    if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, uint64_t(lda) * 2, BM, BK,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, uint64_t(ldb) * 2, BN / 2, BK,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  } else {
+    if (M % 256 != 0) return PB_ERR_BAD_ARG;
+    if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, uint64_t(lda) * 2, BK, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, uint64_t(ldb) * 2, BK, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
+  if (Cfg::kOutF32) {
+    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, uint64_t(ldc) * 4, 32, 16,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+    tmC2 = tmC;
+  } else {
+    if ((rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+    if (MODE == kBiasGeluBf16) {
+      if ((rc = make_tmap_2d(&tmC2, C2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
+                             CU_TENSOR_MAP_SWIZZLE_64B)))
+        return rc;
+    } else {
+      tmC2 = tmC;
+    }
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + 255) / 256;
+  p.n_tiles = N / BN;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.splits = Cfg::kWgrad ? (splits < 1 ? 1 : splits) : 1;
+  if (p.splits > p.k_blocks) p.splits = p.k_blocks;
+  {
+    int per = (p.k_blocks + p.splits - 1) / p.splits;
+    p.splits = (p.k_blocks + per - 1) / per;
+  }
+  p.bias = bias; p.aux = aux; p.aux_period = aux_period > 0 ? aux_period : 1; p.ld_aux = ld_aux;
+  if (!Cfg::kWgrad) {
+    p.lbo_a = 16; p.sbo_a = 1024; p.kstep_a = 32;
+    p.lbo_b = 16; p.sbo_b = 1024; p.kstep_b = 32;
+  } else {
+    p.lbo_a = 8192; p.sbo_a = 1024; p.kstep_a = 2048;
+    p.lbo_b = 8192; p.sbo_b = 1024; p.kstep_b = 2048;
+  }
+  if (g_desc_override.active) {
+    p.lbo_a = g_desc_override.v[0]; p.sbo_a = g_desc_override.v[1]; p.kstep_a = g_desc_override.v[2];
+    p.lbo_b = g_desc_override.v[3]; p.sbo_b = g_desc_override.v[4]; p.kstep_b = g_desc_override.v[5];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+  int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+  if (clusters <= 0) return 0;
+  gemm2_kernel<MODE><<<clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+  PB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_gemm2(int mode, const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
+                 int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits, cudaStream_t stream) {
+  switch (mode) {
+    case kBiasBf16:
+      return launch_gemm2_t<kBiasBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
+    case kBiasGeluBf16:
+      return launch_gemm2_t<kBiasGeluBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits,
+                                           stream);
+    case kRowTabF32:
+      return launch_gemm2_t<kRowTabF32>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
+    case kGeluGradBf16:
+      return launch_gemm2_t<kGeluGradBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits,
+                                           stream);
+    case kWgradF32:
+      return launch_gemm2_t<kWgradF32>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
+    default:
+      return PB_ERR_BAD_ARG;
+  }
+}
+
+}  // namespace pb

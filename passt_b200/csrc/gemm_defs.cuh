@@ -1,0 +1,72 @@
+// passt_b200 — definitions shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+enum GemmMode : int {
+  kBiasBf16 = 0,      // C = bf16(acc + bias)
+  kBiasGeluBf16 = 1,  // C = bf16(gelu'(acc + bias)), C2 = bf16(gelu(acc + bias))
+  kRowTabF32 = 2,     // C = fp32(acc + tab[row % period, col])
+  kGeluGradBf16 = 3,  // C = bf16(acc * aux[row, col])   (aux = gelu'(pre) saved by mode 1)
+  kWgradF32 = 4,      // C += fp32(acc)   (MN-major operands, split-K, TMA reduce-add)
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant, each owning half of the N columns
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+struct GemmParams {
+  int M, N, K;             // D is [M,N]; K = contraction length
+  int m_tiles, n_tiles;    // tile grid
+  int k_blocks;            // total BK blocks along K
+  int splits;              // split-K factor (1 for TN modes)
+  const float* bias;       // [N] or nullptr
+  const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 gelu'(pre) [M, ld_aux]
+  int aux_period;          // mode 2
+  int ld_aux;              // elements
+  // UMMA smem-descriptor strides; exposed so the bring-up test can probe alternatives without a rebuild
+  uint32_t lbo_a, sbo_a, kstep_a;  // bytes
+  uint32_t lbo_b, sbo_b, kstep_b;  // bytes
+};
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact-erf GELU and its derivative from one rcp + one ex2 (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7):
+//   gelu(x) = x * Phi(x),  gelu'(x) = Phi(x) + x * phi(x),  Phi = 0.5 (1 + erf(x / sqrt 2)),  phi = e^{-x^2/2}/sqrt(2 pi)
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float u = x * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, fabsf(u), 1.0f));
+  const float e = fast_ex2(u * u * -1.4426950408889634f);            // exp(-u^2) = exp(-x^2/2)
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float erf_abs = fmaf(-q * t, e, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, u), 0.5f);
+  g = x * cdf;
+  dg = fmaf(x * e, 0.3989422804014327f, cdf);
+}
+
+
+struct DescOverride {
+  int active = 0;
+  uint32_t v[6];
+};
+extern DescOverride g_desc_override;
+
+// 2-CTA (cta_group::2) variant, gemm2.cu.  Returns PB_ERR_BAD_ARG when the shape is not supported.
+int launch_gemm2(int mode, const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
+                 int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits, cudaStream_t stream);
+
+}  // namespace pb

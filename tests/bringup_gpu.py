@@ -324,6 +324,65 @@ def g_attn():
         log(**rec)
 
 
+def g_gemm_2cta():
+    """2-CTA kernel vs torch and vs the 1-CTA kernel (timing A/B)."""
+    lib = L.load()
+    torch.manual_seed(5)
+    for (M, N, K) in [(256, 256, 64), (300, 512, 128), (1000, 768, 768), (30336, 2304, 768), (30336, 768, 3072),
+                      (30336, 3072, 768), (30336, 768, 768)]:
+        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+        bias = torch.randn(N, device=dev)
+        ref = A.float() @ B.float().t() + bias
+        rec = dict(test="gemm2_tn", M=M, N=N, K=K)
+        for two in (1, 0):
+            lib.passt_gemm_set_2cta(two)
+            C = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+            gemm(A, B, C, bias=bias, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, mode=0)
+            torch.cuda.synchronize()
+            rec[f"relerr_{two}"] = relerr(C, ref)
+            if M >= 30000:
+                ms = timeit(lambda: gemm(A, B, C, bias=bias, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, mode=0))
+                rec[f"tflops_{two}"] = 2.0 * M * N * K / ms / 1e9
+        log(**rec)
+    for (Kt, M, N, splits) in [(64, 256, 256, 1), (1000, 768, 768, 4), (30336, 2304, 768, 16), (30336, 768, 3072, 8),
+                               (30336, 3072, 768, 8), (30336, 768, 768, 24)]:
+        A = (torch.randn(Kt, M, device=dev) * 0.5).bfloat16()
+        B = (torch.randn(Kt, N, device=dev) * 0.5).bfloat16()
+        ref = A.float().t() @ B.float()
+        rec = dict(test="gemm2_wgrad", Kt=Kt, M=M, N=N, splits=splits)
+        for two in (1, 0):
+            lib.passt_gemm_set_2cta(two)
+            C = torch.zeros(M, N, device=dev)
+            gemm(A, B, C, M=M, N=N, K=Kt, lda=M, ldb=N, ldc=N, mode=4, splits=splits)
+            torch.cuda.synchronize()
+            rec[f"relerr_{two}"] = relerr(C, ref)
+            if Kt >= 30000:
+                ms = timeit(lambda: gemm(A, B, C, M=M, N=N, K=Kt, lda=M, ldb=N, ldc=N, mode=4, splits=splits))
+                rec[f"tflops_{two}"] = 2.0 * M * N * Kt / ms / 1e9
+        log(**rec)
+    lib.passt_gemm_set_2cta(1)
+
+
+def g_gemm_yardstick():
+    """cuBLAS (torch.matmul) on the same shapes, as a yardstick for what the hardware sustains (not a product path)."""
+    torch.manual_seed(5)
+    lib = L.load()
+    for (M, N, K) in [(30336, 2304, 768), (30336, 768, 3072), (30336, 3072, 768), (30336, 768, 768), (8192, 8192, 8192)]:
+        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+        C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        rec = dict(test="yardstick", M=M, N=N, K=K)
+        ms = timeit(lambda: torch.matmul(A, B.t(), out=C), iters=50)
+        rec["cublas_tflops"] = 2.0 * M * N * K / ms / 1e9
+        for two in (1, 0):
+            lib.passt_gemm_set_2cta(two)
+            ms = timeit(lambda: gemm(A, B, C, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, mode=0), iters=50)
+            rec[f"ours_tflops_{two}"] = 2.0 * M * N * K / ms / 1e9
+        log(**rec)
+    lib.passt_gemm_set_2cta(1)
+
+
 GROUPS = {k[2:]: v for k, v in globals().items() if k.startswith("g_")}
 
 if __name__ == "__main__":
