@@ -119,43 +119,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);
     constexpr uint32_t id_q = make_idesc_bf16(128, 64, 1, 1);
+    // base descriptors are computed once, warp-uniformly; inside the loop an elected lane only adds the per-k offset
+    // (the start-address field is in 16-byte units) and issues the tcgen05 instructions
+    uint64_t bQk[2], bdOk[2], bQmn[2], bdOmn[2], bKmn[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t aQ = smem_u32(sQdO + s * 32768), adO = aQ + 16384;
+      bQk[s] = make_smem_desc_sw128(aQ, 16, 1024);          // Q  as K-major B  (S^T = K Q^T)
+      bdOk[s] = make_smem_desc_sw128(adO, 16, 1024);        // dO as K-major B  (dP^T = V dO^T)
+      bQmn[s] = make_smem_desc_sw128(aQ, 8192, 1024);       // Q  as MN-major B (dK += dS^T Q)
+      bdOmn[s] = make_smem_desc_sw128(adO, 8192, 1024);     // dO as MN-major B (dV += P^T dO)
+      bKmn[s] = make_smem_desc_sw128(smem_u32(sKV + s * 32768), 8192, 1024);   // K as MN-major B (dQ = dS K)
+    }
+    const uint64_t bdST = make_smem_desc_sw128(smem_u32(sdST), 16384, 1024);   // dS^T as MN-major A (dQ = dS K)
     uint32_t g = 0, n = 0;
     for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
       const uint32_t kb = n & 1;
       mbar_wait(kv_ready, n & 1);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sKV + kb * 32768);
-      const uint32_t adST = smem_u32(sdST);
       for (int i = 0; i < n_q; ++i, ++g) {
         const uint32_t s = g & 1;
         mbar_wait(&qdo_full[s], (g >> 1) & 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQdO + s * 32768), adO = aQ + 16384;
-        if (lane == 0) {
+        if (elect_one()) {
+          const uint64_t qk = s ? bQk[1] : bQk[0], dok = s ? bdOk[1] : bdOk[0];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tS, tK + k * 8, make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tK + k * 8, qk + uint64_t(k * 2), id_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tdP, tV + k * 8, make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tdP, tV + k * 8, dok + uint64_t(k * 2), id_s, k > 0);
           tc_commit(sdp_full);
         }
         __syncwarp();
         mbar_wait(pds_full, g & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
+          const uint64_t qmn = s ? bQmn[1] : bQmn[0], domn = s ? bdOmn[1] : bdOmn[0];
+          const uint64_t kmn = kb ? bKmn[1] : bKmn[0];
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // contraction = queries; 16 queries = 8 TMEM columns of packed bf16
-            umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(adO + k * 2048, 8192, 1024),
-                         id_kv, (i > 0 || k > 0));
+            umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, domn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(aQ + k * 2048, 8192, 1024),
-                         id_kv, (i > 0 || k > 0));
+            umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, qmn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
-            umma_bf16_ss(tdQ, make_smem_desc_sw128(adST + k * 2048, 16384, 1024),
-                         make_smem_desc_sw128(aK + k * 2048, 8192, 1024), id_q, k > 0);
+            umma_bf16_ss(tdQ, bdST + uint64_t(k * 128), kmn + uint64_t(k * 128), id_q, k > 0);
           tc_commit(dq_full);
           tc_commit(&qdo_empty[s]);
           if (i == n_q - 1) {

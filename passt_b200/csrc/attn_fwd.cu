@@ -5,18 +5,18 @@
 // as nn.Linear(dim, 3*dim) lays it out (:345 reshape(B, N, 3, H, hd)); output is [B, N, H*64] (bf16), i.e. the
 // (attn @ v).transpose(1, 2).reshape(B, N, C) layout (:358), plus the per-row log-sum-exp for the backward pass.
 //
-// One CTA = one (128-query tile, head, clip).  Warp roles:
-//   warp 0    : TMA producer (Q once, K/V tiles through a 2-stage ring; OOB rows are zero-filled by TMA)
-//   warp 1    : TMEM allocator + tcgen05.mma issuer
+// Persistent CTAs walk a strided list of (128-query tile, head, clip) items.  Warp roles:
+//   warp 0    : TMA producer (Q tiles and K/V tiles through 2-stage rings, running ahead across items)
+//   warp 1    : TMEM allocator + tcgen05.mma issuer (descriptors precomputed; an elected lane only issues)
 //   warps 2-5 : softmax, one thread per query row (tcgen05.ld 32x32b)
-// Both MMAs take their A operand from TENSOR MEMORY (the M=128 x N<=128 shapes are operand-bandwidth bound when A
-// comes from shared memory):
-//   S   = Q K^T  : A = Q copied once into TMEM (32 columns of packed bf16), B = K tile (smem, K-major)
-//   O_j = P_j V_j: A = P_j written by the softmax threads with tcgen05.st over the first 64 columns of the S
-//                  accumulator they have just consumed, B = V tile (smem, MN-major view of the [keys, hd] tile)
-// Online softmax (running max / sum) and the O accumulator live in registers.
-// TMEM columns: S/P [0,128)  O_j [128,192)  Q [192,224)  -> 256 allocated, two CTAs co-reside per SM so one CTA's
-// softmax overlaps the other's MMAs.
+//   S   = Q K^T  : A = Q tile (smem, K-major), B = K tile (smem, K-major)              -> TMEM [0,128)
+//   O  += P_j V_j: A = P_j in TENSOR MEMORY (bf16 pairs written by the softmax threads) -> TMEM [192,256),
+//                  B = V tile (smem, MN-major view of the [keys, hd] tile); O accumulates in TMEM across key tiles
+// Softmax is single-pass with a lagged reference maximum (FA4-style): probabilities of tile j are taken relative to
+// the maximum known before the tile; the running sum and the TMEM-resident O are rescaled only when the maximum
+// grows by more than 2^8, and a guarded slow path redoes a tile whose scores exceed the reference by more than 2^64
+// (exactness is preserved in every case; bf16/fp32 have the exponent range for the lag).
+// TMEM columns: S [0,128)  P [128,192)  O [192,256) -> 256 allocated, two CTAs co-reside per SM.
 #include "common.cuh"
 
 namespace pb {
@@ -33,7 +33,12 @@ struct AttnFwdParams {
   float scale_log2;  // softmax scale * log2(e)
   float scale;
   float* lse;        // [B, H, N] natural-log LSE of the scaled scores
+  long long* timeline;  // bring-up only: clock64 stamps of CTA 0 (nullptr in production)
 };
+#define PB_STAMP(role, idx)                                                                     \
+  do {                                                                                           \
+    if (p.timeline != nullptr && blockIdx.x == 0 && (idx) < 512) p.timeline[(role) * 512 + (idx)] = clock64(); \
+  } while (0)
 
 struct AttnFwdSmem {
   static constexpr int kQ = 0;                                       // 2 Q tiles (ring); reused as output staging
@@ -59,7 +64,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* s_full = bars + 8;        // [1]
   uint64_t* p_full = bars + 9;        // [1]  (128 softmax threads arrive)
   uint64_t* o_full = bars + 10;       // [1]
-  uint64_t* q_ready = bars + 11;      // [1]  (128 arrivals: Q is in TMEM)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,7 +79,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
-    mbar_init(q_ready, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_holder);
@@ -84,9 +87,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tmem_S = tmem_base;         // fp32 scores, 128 columns
-  const uint32_t tmem_P = tmem_base;         // bf16 probabilities over the consumed scores, 64 columns
-  const uint32_t tmem_O = tmem_base + 128;   // fp32 partial output, 64 columns
-  const uint32_t tmem_Q = tmem_base + 192;   // bf16 queries, 32 columns
+  const uint32_t tmem_P = tmem_base + 128;   // bf16 probabilities (pairs), 64 columns
+  const uint32_t tmem_O = tmem_base + 192;   // fp32 output accumulator, 64 columns
   const int C = p.H * kHd;
 
   if (warp == 0) {
@@ -101,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int j = 0; j < n_kv; ++j, ++t) {
           const uint32_t s = t & 1;
           mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+          PB_STAMP(2, t);
           uint8_t* sK = sKV + s * (2 * kKvTile * kHd * 2);
           uint8_t* sV = sK + kKvTile * kHd * 2;
           mbar_arrive_expect_tx(&kv_full[s], 2 * kKvTile * kHd * 2);
@@ -110,43 +113,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S = Q K^T : A TMEM, B K-major
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S = Q K^T : A, B K-major (smem)
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // O = P V   : A TMEM, B (V) MN-major
-    auto issue_s = [&](uint32_t t) {
+    // all shared-memory descriptors are computed once, warp-uniformly, outside the critical path; inside the loop an
+    // elected lane only issues the tcgen05 instructions
+    uint64_t dQ[2][4], dK[2][4], dV[2][8];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t aQ = smem_u32(sQ + s * (kQTile * kHd * 2));
+      const uint32_t aK = smem_u32(sKV + s * (2 * kKvTile * kHd * 2));
+      const uint32_t aV = aK + kKvTile * kHd * 2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dQ[s][k] = make_smem_desc_sw128(aQ + k * 32, 16, 1024);
+        dK[s][k] = make_smem_desc_sw128(aK + k * 32, 16, 1024);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dV[s][k] = make_smem_desc_sw128(aV + k * 2048, 8192, 1024);
+    }
+    auto issue_s = [&](uint32_t t, uint32_t qs) {
       const uint32_t s = t & 1;
       mbar_wait(&kv_full[s], (t >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t aK = smem_u32(sKV + s * (2 * kKvTile * kHd * 2));
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHd / 16; ++k)
-          umma_bf16_ts(tmem_S, tmem_Q + k * 8, make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s,
-                       k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_S, qs ? dQ[1][k] : dQ[0][k], s ? dK[1][k] : dK[0][k], idesc_s, k > 0 ? 1u : 0u);
         tc_commit(s_full);
       }
       __syncwarp();
     };
     uint32_t t = 0, n = 0;
     for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
-      mbar_wait(q_ready, n & 1);
-      tc_fence_after();
-      issue_s(t);
+      const uint32_t qs = n & 1;
+      const bool has_next = (it + int(gridDim.x) < p.total_items);
+      mbar_wait(&q_full[qs], (n >> 1) & 1);
+      if (n == 0) issue_s(t, qs);              // later items: S of their first tile was issued ahead (below)
       for (int j = 0; j < n_kv; ++j, ++t) {
         const uint32_t s = t & 1;
-        mbar_wait(p_full, t & 1);   // P_t is in TMEM, the previous O has been drained
+        mbar_wait(p_full, t & 1);   // P_t is in TMEM and S_t has been consumed
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t aV = smem_u32(sKV + s * (2 * kKvTile * kHd * 2) + kKvTile * kHd * 2);
+        if (lane == 0) PB_STAMP(1, t * 3 + 0);
+        // next scores first (the softmax warps can start on them while PV_t runs)
+        if (j + 1 < n_kv) {
+          issue_s(t + 1, qs);
+        } else if (has_next) {
+          mbar_wait(&q_full[qs ^ 1], ((n + 1) >> 1) & 1);
+          issue_s(t + 1, qs ^ 1);
+        }
+        if (lane == 0) PB_STAMP(1, t * 3 + 1);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kKvTile / 16; ++k)
-            umma_bf16_ts(tmem_O, tmem_P + k * 8, make_smem_desc_sw128(aV + k * 2048, 8192, 1024), idesc_o,
-                         k > 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_ts(tmem_O, tmem_P + k * 8, s ? dV[1][k] : dV[0][k], idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           tc_commit(o_full);
           tc_commit(&kv_empty[s]);
         }
         __syncwarp();
-        // S_{t+1} overwrites the columns P_t lives in: issue order (after PV_t) keeps it safe
-        if (j + 1 < n_kv) issue_s(t + 1);
+        if (lane == 0) PB_STAMP(1, t * 3 + 2);
       }
     }
   } else {
@@ -154,59 +178,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int q = warp & 3;
     const int r = q * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    // Q tile of item n: swizzled smem row -> packed bf16 in TMEM (A operand of S = Q K^T)
-    auto stage_q = [&](uint32_t n) {
-      const uint32_t qs = n & 1;
-      mbar_wait(&q_full[qs], (n >> 1) & 1);
-      const uint8_t* src = sQ + qs * (kQTile * kHd * 2);
-      uint32_t qv[32];
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint4 u = *reinterpret_cast<const uint4*>(src + r * 128 + ((ch ^ (r & 7)) << 4));
-        qv[ch * 4] = u.x; qv[ch * 4 + 1] = u.y; qv[ch * 4 + 2] = u.z; qv[ch * 4 + 3] = u.w;
-      }
-      tmem_st_x32(tmem_Q + lane_addr, qv);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(q_ready);
-    };
+    constexpr float kRescaleTh = 8.0f;     // lagged-max: rescale O / l only when the maximum grew by > 2^8
+    constexpr float kGuardTh = 64.0f;      // redo a tile whose scores exceed the reference by more than 2^64
     uint32_t t = 0, n = 0;
-    if (blockIdx.x < p.total_items) stage_q(0);
     for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
       const int qt = it % p.n_qt, h = (it / p.n_qt) % p.H, b = it / (p.n_qt * p.H);
       const int q0 = qt * kQTile;
-      float m_run = -INFINITY, l_run = 0.f;
-      float o_acc[kHd];
-#pragma unroll
-      for (int i = 0; i < kHd; ++i) o_acc[i] = 0.f;
+      float m_used = 0.f, m_seen = 0.f, l_run = 0.f;     // scaled (log2) units
 
       for (int j = 0; j < n_kv; ++j, ++t) {
         const int kv_valid = min(kKvTile, p.N - j * kKvTile);
         const bool full_tile = (kv_valid == kKvTile);     // warp-uniform: only the last key tile needs masking
         mbar_wait(s_full, t & 1);
         tc_fence_after();
-        // pass 1: row max
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        if (warp == 2 && lane == 0) PB_STAMP(0, t * 5 + 0);
+        if (j == 0) {
+          // reference maximum of a new row: the first 32 scores (key 0 is always valid)
           uint32_t v[32];
-          tmem_ld_x32(tmem_S + lane_addr + c * 32, v);
+          tmem_ld_x32(tmem_S + lane_addr, v);
           tmem_ld_wait();
-          if (full_tile) {
+          float mx = __uint_as_float(v[0]);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-        }
-        const float m_new = fmaxf(m_run, mx);
-        const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
-        const float moff = m_new * p.scale_log2;
-        // drain the previous partial O: S_t was issued after PV_{t-1}, so it is complete (the wait is immediate)
-        if (j > 0) {
+          for (int i = 1; i < 32; ++i)
+            if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          m_used = mx * p.scale_log2;
+          m_seen = m_used;
+        } else if (__any_sync(0xffffffffu, m_seen - m_used > kRescaleTh)) {
+          // rare: bring l and the TMEM accumulator to the new reference (PV_{t-1} must have landed)
+          const float alpha = ex2_approx(m_used - m_seen);     // == 1 for rows whose maximum did not move
           mbar_wait(o_full, (t - 1) & 1);
           tc_fence_after();
 #pragma unroll
@@ -215,75 +214,113 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tmem_ld_x32(tmem_O + lane_addr + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_x32(tmem_O + lane_addr + c * 32, v);
           }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_used = m_seen;
         }
-        // pass 2: P = exp2(S*c - m*c) -> packed bf16 -> TMEM, over the score columns already consumed
-        float rs0 = 0.f, rs1 = 0.f;
+        if (warp == 2 && lane == 0) PB_STAMP(0, t * 5 + 1);
+        // single pass: P = exp2(S*c - m_used) -> bf16 pairs -> TMEM; track the tile maximum on the side
+        bool redo = false;
+        do {
+          float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_S + lane_addr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          if (full_tile) {
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_S + lane_addr + c * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            if (full_tile) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff));
-              rs0 += e0;
-              rs1 += e1;
-              pk[i >> 1] = pack_bf16(e0, e1);
+              for (int i = 0; i < 32; i += 2) {
+                const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                mx0 = fmaxf(mx0, s0);
+                mx1 = fmaxf(mx1, s1);
+                const float e0 = ex2_approx(fmaf(s0, p.scale_log2, -m_used));
+                const float e1 = ex2_approx(fmaf(s1, p.scale_log2, -m_used));
+                rs0 += e0;
+                rs1 += e1;
+                pk[i >> 1] = pack_bf16(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const bool ok0 = c * 32 + i < kv_valid, ok1 = c * 32 + i + 1 < kv_valid;
+                const float s0 = ok0 ? __uint_as_float(v[i]) : -INFINITY;
+                const float s1 = ok1 ? __uint_as_float(v[i + 1]) : -INFINITY;
+                mx0 = fmaxf(mx0, s0);
+                mx1 = fmaxf(mx1, s1);
+                const float e0 = ex2_approx(fmaf(s0, p.scale_log2, -m_used));   // exp2(-inf) = 0 for masked keys
+                const float e1 = ex2_approx(fmaf(s1, p.scale_log2, -m_used));
+                rs0 += e0;
+                rs1 += e1;
+                pk[i >> 1] = pack_bf16(e0, e1);
+              }
             }
+            tmem_st_x16(tmem_P + lane_addr + c * 16, pk);
+          }
+          const float tile_max = fmaxf(mx0, mx1) * p.scale_log2;
+          redo = false;
+          if (__any_sync(0xffffffffu, tile_max - m_used > kGuardTh)) {
+            // guarded slow path (scores far above the reference): move the reference and redo this tile; S is intact
+            const float m_new = fmaxf(m_used, tile_max);
+            const float alpha = ex2_approx(m_used - m_new);
+            if (j > 0) {
+              mbar_wait(o_full, (t - 1) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld_x32(tmem_O + lane_addr + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st_x32(tmem_O + lane_addr + c * 32, v);
+              }
+              tmem_st_wait();
+            }
+            l_run *= alpha;
+            m_used = m_new;
+            m_seen = fmaxf(m_seen, m_new);
+            redo = true;
           } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff));
-              float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -moff));
-              e0 = (c * 32 + i < kv_valid) ? e0 : 0.f;
-              e1 = (c * 32 + i + 1 < kv_valid) ? e1 : 0.f;
-              rs0 += e0;
-              rs1 += e1;
-              pk[i >> 1] = pack_bf16(e0, e1);
-            }
+            l_run += rs0 + rs1;
+            m_seen = fmaxf(m_seen, tile_max);
           }
-          tmem_st_x16(tmem_P + lane_addr + c * 16, pk);
-        }
-        l_run = l_run * alpha + (rs0 + rs1);
-        m_run = m_new;
+        } while (redo);
+        if (warp == 2 && lane == 0) PB_STAMP(0, t * 5 + 3);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full);
+        if (warp == 2 && lane == 0) PB_STAMP(0, t * 5 + 4);
       }
-      // every S MMA of this item has completed (s_full of its last tile): the Q columns are free -> stage the next Q
-      // now so the MMA warp can start the next item while this one's epilogue runs
-      const bool has_next = (it + int(gridDim.x) < p.total_items);
-      if (has_next) stage_q(n + 1);
-      // last partial O
+      // ---- item epilogue: O (TMEM) / l -> bf16 -> swizzled staging (this item's Q buffer) -> TMA store
       mbar_wait(o_full, (t - 1) & 1);
       tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      if (q0 + r < p.N)
+        p.lse[(size_t(b) * p.H + h) * p.N + q0 + r] = (m_used + log2f(l_run)) * 0.6931471805599453f;
+      uint8_t* stage = sQ + (n & 1) * (kQTile * kHd * 2) + q * 4096;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_O + lane_addr + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(v[i]);
+        for (int g = 0; g < 4; ++g) {
+          const int ch = c * 4 + g;
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+          o.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+          o.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+          o.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
+        }
       }
-      const float inv_l = 1.0f / l_run;
-      if (q0 + r < p.N)
-        p.lse[(size_t(b) * p.H + h) * p.N + q0 + r] = m_run * p.scale + logf(l_run);
-      // O tile -> swizzled staging (this item's Q buffer: Q has lived in TMEM since the item started) -> TMA store
-      uint8_t* stage = sQ + (n & 1) * (kQTile * kHd * 2) + q * 4096;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 o;
-        o.x = pack_bf16(o_acc[ch * 8 + 0] * inv_l, o_acc[ch * 8 + 1] * inv_l);
-        o.y = pack_bf16(o_acc[ch * 8 + 2] * inv_l, o_acc[ch * 8 + 3] * inv_l);
-        o.z = pack_bf16(o_acc[ch * 8 + 4] * inv_l, o_acc[ch * 8 + 5] * inv_l);
-        o.w = pack_bf16(o_acc[ch * 8 + 6] * inv_l, o_acc[ch * 8 + 7] * inv_l);
-        *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) = o;
-      }
+      // O has been read: the next item's first PV (accumulate = 0) may overwrite it.  That MMA needs this thread's
+      // p_full arrival for the next tile, which comes later in program order, so no extra barrier is required.
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
@@ -303,9 +340,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+long long* g_attn_timeline = nullptr;
+
 }  // namespace pb
 
 extern "C" {
+// bring-up: device buffer of >= 3*512 int64 receiving clock64 stamps of CTA 0 (NULL disables)
+void passt_attn_debug_timeline(void* buf) { pb::g_attn_timeline = reinterpret_cast<long long*>(buf); }
+
 
 // qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, N]
 int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream) {
@@ -324,6 +366,7 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   p.N = N; p.H = H; p.B = B; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.lse = lse;
   p.n_qt = (N + kQTile - 1) / kQTile;
   p.total_items = B * H * p.n_qt;
+  p.timeline = pb::g_attn_timeline;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -383,6 +383,33 @@ def g_gemm_yardstick():
     lib.passt_gemm_set_2cta(1)
 
 
+def g_attn_timeline():
+    """clock64 timeline of CTA 0 of the forward attention kernel (softmax thread / MMA lane / TMA producer)."""
+    torch.manual_seed(4)
+    B, N, H, hd = 64, 474, 12, 64
+    C = H * hd
+    qkv = torch.randn(B, N, 3 * C, device=dev).bfloat16()
+    out = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=dev)
+    tl = torch.zeros(3 * 512, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, hd ** -0.5, L.stream_ptr())
+    L.load().passt_attn_debug_timeline(L.ptr(tl))
+    L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, hd ** -0.5, L.stream_ptr())
+    torch.cuda.synchronize()
+    L.load().passt_attn_debug_timeline(None)
+    t = tl.cpu().tolist()
+    sm, mm, pr = t[0:512], t[512:1024], t[1024:1536]
+    t0 = min(x for x in sm + mm + pr if x > 0)
+    rows = []
+    for k in range(16):
+        s = [x - t0 if x else None for x in sm[k * 5:k * 5 + 5]]
+        m = [x - t0 if x else None for x in mm[k * 3:k * 3 + 3]]
+        rows.append(dict(tile=k, softmax=s, mma=m, prod=(pr[k] - t0) if pr[k] else None))
+    log(test="attn_timeline", legend="softmax: s_full|pass1|Odrain|pass2|arrive ; mma: p_full|PV issued|S next issued ; prod: kv slot free",
+        rows=rows)
+
+
 GROUPS = {k[2:]: v for k, v in globals().items() if k.startswith("g_")}
 
 if __name__ == "__main__":
