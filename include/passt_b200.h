@@ -44,10 +44,12 @@ void passt_gemm_set_2cta(int enable);
 void passt_gemm_debug_desc(int active, const unsigned* v6);
 
 /* ---- attention: softmax(q k^T * scale) v, models/passt.py:345-358, and its autograd ---------------------------- */
-/* qkv bf16 [B,N,3*H*64] (layout of nn.Linear(dim,3*dim) output, :345) -> out bf16 [B,N,H*64], lse f32 [B,H,N] */
+/* qkv bf16 [B,N,3*H*64] (layout of nn.Linear(dim,3*dim) output, :345) -> out bf16 [B,N,H*64],
+ * lse f32 [B,H,Npad] (Npad = 128*ceil(N/128); log2-domain log-sum-exp of the scaled scores, pad rows +inf) */
 int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream);
 /* bring-up hook: device buffer (>= 3*512 int64) receiving clock64 stamps of CTA 0 of attn_fwd; NULL disables */
 void passt_attn_debug_timeline(void* buf);
+void passt_attn_bwd_debug_timeline(void* buf);
 size_t passt_attn_bwd_workspace_bytes(int B, int N, int H);
 int passt_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
                    void* workspace, int B, int N, int H, float scale, void* stream);

@@ -30,9 +30,16 @@ struct AttnBwdParams {
   int n_kvt;         // key tiles per (clip, head)
   int total_items;   // B * H * n_kvt
   float scale_log2, scale;
-  const float* lse;   // [B,H,N]
-  const float* Dsum;  // [B,H,N]
+  const float* lse;   // [B,H,Npad] log2 domain, pad rows +inf
+  const float* Dsum;  // [B,H,Npad] pad rows 0
+  float* dq_acc;      // [B,N,C] fp32 accumulation of dQ over key tiles
+  int Npad;
+  long long* timeline;  // bring-up only: clock64 stamps of CTA 0 (nullptr in production)
 };
+#define PB_STAMP(role, idx)                                                                     \
+  do {                                                                                           \
+    if (p.timeline != nullptr && blockIdx.x == 0 && (idx) < 512) p.timeline[(role) * 512 + (idx)] = clock64(); \
+  } while (0)
 
 struct AttnBwdSmem {
   static constexpr int kKV = 0;                      // 2 item buffers x (K 16 KB + V 16 KB)
@@ -109,9 +116,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int i = 0; i < n_q; ++i, ++g) {
           const uint32_t s = g & 1;
           mbar_wait(&qdo_empty[s], ((g >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&qdo_full[s], 2 * 16384);
+          mbar_arrive_expect_tx(&qdo_full[s], 2 * 16384 + 2 * 512);
           tma_load_3d(sQdO + s * 32768, &tmQKV, &qdo_full[s], h * kBHd, i * kTile, b);
           tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, &qdo_full[s], h * kBHd, i * kTile, b);
+          const size_t voff = (size_t(b) * p.H + h) * p.Npad + size_t(i) * kTile;
+          bulk_load_1d(sVec + s * 256, p.lse + voff, 512, &qdo_full[s]);
+          bulk_load_1d(sVec + s * 256 + 128, p.Dsum + voff, 512, &qdo_full[s]);
         }
       }
     }
@@ -141,6 +151,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const uint32_t s = g & 1;
         mbar_wait(&qdo_full[s], (g >> 1) & 1);
         tc_fence_after();
+        if (lane == 0) PB_STAMP(1, g * 4 + 0);
         if (elect_one()) {
           const uint64_t qk = s ? bQk[1] : bQk[0], dok = s ? bdOk[1] : bdOk[0];
 #pragma unroll
@@ -150,21 +161,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tc_commit(sdp_full);
         }
         __syncwarp();
+        if (lane == 0) PB_STAMP(1, g * 4 + 1);
         mbar_wait(pds_full, g & 1);
         tc_fence_after();
+        if (lane == 0) PB_STAMP(1, g * 4 + 2);
         if (elect_one()) {
           const uint64_t qmn = s ? bQmn[1] : bQmn[0], domn = s ? bdOmn[1] : bdOmn[0];
           const uint64_t kmn = kb ? bKmn[1] : bKmn[0];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
+            umma_bf16_ss(tdQ, bdST + uint64_t(k * 128), kmn + uint64_t(k * 128), id_q, k > 0);
+          tc_commit(dq_full);           // dQ first: the compute warps drain it while dV / dK accumulate
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // contraction = queries; 16 queries = 8 TMEM columns of packed bf16
             umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, domn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, qmn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
-            umma_bf16_ss(tdQ, bdST + uint64_t(k * 128), kmn + uint64_t(k * 128), id_q, k > 0);
-          tc_commit(dq_full);
           tc_commit(&qdo_empty[s]);
           if (i == n_q - 1) {
             tc_commit(dkv_full);
@@ -172,6 +185,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         }
         __syncwarp();
+        if (lane == 0) PB_STAMP(1, g * 4 + 3);
       }
     }
   } else {
@@ -182,7 +196,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int r = q * 32 + lane;        // row inside the tile (key row for S^T/dP^T, query row for dQ)
     const int ct = threadIdx.x - 64;    // 0..255
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    const float log2e = 1.4426950408889634f;
     // K (warps with hc == 0) and V (hc == 1) rows of item n: swizzled smem -> packed bf16 in TMEM
     auto stage_kv = [&](uint32_t n) {
       const uint32_t kb = n & 1;
@@ -207,19 +220,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const bool has_next = (it + int(gridDim.x) < p.total_items);
       for (int i = 0; i < n_q; ++i, ++g) {
         const int q0 = i * kTile;
-        float* s_lse = sVec + (g & 1) * 256;
-        float* s_D = s_lse + 128;
-        if (ct == 0) tma_store_wait_read<0>();   // staging (dQ of the previous step / dK,dV of the previous item) was read
-        if (ct < 128) {
-          const int qq = q0 + ct;
-          s_lse[ct] = qq < p.N ? p.lse[(size_t(b) * p.H + h) * p.N + qq] * log2e : INFINITY;
-        } else {
-          const int qq = q0 + ct - 128;
-          s_D[ct - 128] = qq < p.N ? p.Dsum[(size_t(b) * p.H + h) * p.N + qq] : 0.f;
-        }
-        named_bar_sync(1, 256);
+        const float* s_lse = sVec + (g & 1) * 256;     // log2-domain LSE of this query tile (TMA bulk copy)
+        const float* s_D = s_lse + 128;
+        mbar_wait(&qdo_full[g & 1], (g >> 1) & 1);     // lse / D landed with the Q / dO tiles
+        if (ct == 0) PB_STAMP(0, g * 6 + 0);
         mbar_wait(sdp_full, g & 1);
         tc_fence_after();
+        if (ct == 0) PB_STAMP(0, g * 6 + 1);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col0 = hc * 64 + c * 32;
@@ -252,16 +259,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 make_uint4(dd2[gq * 4], dd2[gq * 4 + 1], dd2[gq * 4 + 2], dd2[gq * 4 + 3]);
           }
         }
+        if (ct == 0) PB_STAMP(0, g * 6 + 2);
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(pds_full);
+        if (ct == 0) PB_STAMP(0, g * 6 + 3);
         // all S^T / dP^T MMAs of this item are complete after its last sdp_full: K/V columns are free -> stage the
         // next item's K/V now so its first MMAs overlap this item's tail
         if (i == n_q - 1 && has_next) stage_kv(n + 1);
         // ---- drain dQ_i (rows = queries) -> fp32 staging -> TMA reduce-add into the accumulation buffer
         mbar_wait(dq_full, g & 1);
         tc_fence_after();
+        if (ct == 0) PB_STAMP(0, g * 6 + 4);
+        if (ct == 0) tma_store_wait_read<0>();   // staging (dQ of the previous step / dK,dV of the previous item) was read
+        named_bar_sync(1, 256);
         {
           uint32_t v[32];
           tmem_ld_x32(tdQ + lane_addr + hc * 32, v);
@@ -277,10 +289,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         fence_proxy_async();
         named_bar_sync(1, 256);
         if (ct == 0) {
+          // TMA reduce-add of the dQ tile (rows = queries) into the fp32 accumulation buffer; rows >= N are clipped
           tma_reduce_add_3d(&tmdQacc, sdQ, h * kBHd, q0, b);
           tma_reduce_add_3d(&tmdQacc, sdQ + 16384, h * kBHd + 32, q0, b);
           tma_store_commit();
         }
+        if (ct == 0) PB_STAMP(0, g * 6 + 5);
       }
       // ---- item epilogue: dK (scaled), dV -> bf16 -> staging (dQ staging buffer) -> TMA store
       mbar_wait(dkv_full, n & 1);
@@ -325,10 +339,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+long long* g_attn_bwd_timeline = nullptr;
+
 // D[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]     (one warp per token, 8 lanes per head)
 __global__ void __launch_bounds__(256)
 attn_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, float* __restrict__ Dsum,
-                 int B, int N, int H) {
+                 int B, int N, int H, int Npad) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * N) return;
   const int b = gw / N, n = gw - b * N;
@@ -351,7 +367,7 @@ attn_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __res
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if ((lane & 7) == 0 && col < C) Dsum[(size_t(b) * H + col / kBHd) * N + n] = s;
+    if ((lane & 7) == 0 && col < C) Dsum[(size_t(b) * H + col / kBHd) * Npad + n] = s;
   }
 }
 
@@ -374,11 +390,15 @@ attn_dq_pack_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d
 
 extern "C" {
 
+void passt_attn_bwd_debug_timeline(void* buf) { pb::g_attn_bwd_timeline = reinterpret_cast<long long*>(buf); }
+
 size_t passt_attn_bwd_workspace_bytes(int B, int N, int H) {
-  return size_t(B) * N * H * 64 * 4 + size_t(B) * H * N * 4 + 256;
+  const size_t npad = size_t((N + 127) / 128) * 128;
+  return size_t(B) * N * H * 64 * 4 + size_t(B) * H * npad * 4 + 256;
 }
 
-// qkv bf16 [B,N,3C], o bf16 [B,N,C], dO bf16 [B,N,C], lse fp32 [B,H,N] -> dqkv bf16 [B,N,3C]
+// qkv bf16 [B,N,3C], o bf16 [B,N,C], dO bf16 [B,N,C], lse fp32 [B,H,Npad] (log2 domain, from passt_attn_fwd)
+// -> dqkv bf16 [B,N,3C]
 int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, void* workspace,
                    int B, int N, int H, float scale, void* stream) {
   using namespace pb;
@@ -387,11 +407,13 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   const int C = H * kBHd;
   float* dq_acc = reinterpret_cast<float*>(workspace);
   float* Dsum = dq_acc + size_t(B) * N * C;
-  PB_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, size_t(B) * N * C * 4, st));
+  const int Npad = ((N + kTile - 1) / kTile) * kTile;
+  // one memset covers dq_acc and the padded D buffer (pad rows of D must be finite: 0 * NaN would poison dS)
+  PB_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, size_t(B) * N * C * 4 + size_t(B) * H * Npad * 4, st));
   {
     const long long warps = (long long)B * N;
     attn_dsum_kernel<<<int((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o,
-                                                                    (const __nv_bfloat16*)dO, Dsum, B, N, H);
+                                                                    (const __nv_bfloat16*)dO, Dsum, B, N, H, Npad);
     PB_LAUNCH_CHECK();
   }
   CUtensorMap tmQKV, tmdO, tmdQKV, tmdQacc;
@@ -412,6 +434,9 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   p.N = N; p.H = H; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.lse = lse; p.Dsum = Dsum;
   p.n_kvt = (N + kTile - 1) / kTile;
   p.total_items = B * H * p.n_kvt;
+  p.Npad = p.n_kvt * kTile;
+  p.dq_acc = dq_acc;
+  p.timeline = pb::g_attn_bwd_timeline;
   static bool attr_set = false;
   if (!attr_set) {
     PB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -32,7 +32,7 @@ struct AttnFwdParams {
   int total_items;   // B * H * n_qt
   float scale_log2;  // softmax scale * log2(e)
   float scale;
-  float* lse;        // [B, H, N] natural-log LSE of the scaled scores
+  float* lse;        // [B, H, Npad] log2-domain LSE of the scaled scores (Npad = 128*ceil(N/128); pad rows = +inf)
   long long* timeline;  // bring-up only: clock64 stamps of CTA 0 (nullptr in production)
 };
 #define PB_STAMP(role, idx)                                                                     \
@@ -300,8 +300,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(o_full, (t - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
-      if (q0 + r < p.N)
-        p.lse[(size_t(b) * p.H + h) * p.N + q0 + r] = (m_used + log2f(l_run)) * 0.6931471805599453f;
+      // log2-domain LSE, padded rows get +inf (the backward pass turns them into P = 0)
+      p.lse[(size_t(b) * p.H + h) * (size_t(p.n_qt) * kQTile) + q0 + r] =
+          (q0 + r < p.N) ? (m_used + log2f(l_run)) : INFINITY;
       uint8_t* stage = sQ + (n & 1) * (kQTile * kHd * 2) + q * 4096;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -349,7 +350,7 @@ extern "C" {
 void passt_attn_debug_timeline(void* buf) { pb::g_attn_timeline = reinterpret_cast<long long*>(buf); }
 
 
-// qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, N]
+// qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, Npad], Npad = 128*ceil(N/128), log2 domain
 int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0) return PB_ERR_BAD_ARG;

@@ -204,7 +204,7 @@ class PasstFunction(torch.autograd.Function):
             qkv = torch.empty(M, 3 * Dm, **b16)
             _gemm(h1, wqkv, qkv, bias=P[pre + "attn.qkv.bias"], M=M, N=3 * Dm, K=Dm, lda=Dm, ldb=Dm, ldc=3 * Dm, mode=0)
             att = torch.empty(M, Dm, **b16)
-            lse = torch.empty(B, H, ntok, **f32)
+            lse = torch.empty(B, H, ((ntok + 127) // 128) * 128, **f32)   # log2-domain, padded to whole query tiles
             L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(att), L.ptr(lse), B, ntok, H, scale, st)
             oproj = torch.empty(M, Dm, **b16)
             _gemm(att, wproj, oproj, bias=P[pre + "attn.proj.bias"], M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)

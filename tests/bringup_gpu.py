@@ -288,7 +288,8 @@ def g_attn():
     for (B, N) in [(2, 128), (2, 130), (2, 474), (1, 1190), (64, 474)]:
         qkv = (torch.randn(B, N, 3 * C, device=dev)).bfloat16()
         out = torch.full((B, N, C), float("nan"), device=dev, dtype=torch.bfloat16)
-        lse = torch.empty(B, H, N, device=dev)
+        Npad = ((N + 127) // 128) * 128
+        lse = torch.empty(B, H, Npad, device=dev)
         L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, scale, L.stream_ptr())
         torch.cuda.synchronize()
         rec = dict(test="attn_fwd", B=B, N=N)
@@ -298,7 +299,8 @@ def g_attn():
             att = (q @ k.transpose(-2, -1)) * scale
             ref_lse = torch.logsumexp(att, -1)
             ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
-            rec.update(o=relerr(out, ref), lse=relerr(lse, ref_lse), nan=int(torch.isnan(out.float()).sum()))
+            rec.update(o=relerr(out, ref), lse=relerr(lse[:, :, :N] * 0.6931471805599453, ref_lse),
+                       nan=int(torch.isnan(out.float()).sum()))
         else:
             ms = timeit(lambda: L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, scale, L.stream_ptr()))
             rec.update(ms=ms, tflops=4.0 * B * H * N * N * hd / ms / 1e9)
@@ -390,7 +392,7 @@ def g_attn_timeline():
     C = H * hd
     qkv = torch.randn(B, N, 3 * C, device=dev).bfloat16()
     out = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
-    lse = torch.empty(B, H, N, device=dev)
+    lse = torch.empty(B, H, 512, device=dev)
     tl = torch.zeros(3 * 512, dtype=torch.int64, device=dev)
     for _ in range(3):
         L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, hd ** -0.5, L.stream_ptr())
@@ -407,6 +409,38 @@ def g_attn_timeline():
         m = [x - t0 if x else None for x in mm[k * 3:k * 3 + 3]]
         rows.append(dict(tile=k, softmax=s, mma=m, prod=(pr[k] - t0) if pr[k] else None))
     log(test="attn_timeline", legend="softmax: s_full|pass1|Odrain|pass2|arrive ; mma: p_full|PV issued|S next issued ; prod: kv slot free",
+        rows=rows)
+
+
+def g_attn_bwd_timeline():
+    torch.manual_seed(4)
+    B, N, H, hd = 64, 474, 12, 64
+    C = H * hd
+    qkv = torch.randn(B, N, 3 * C, device=dev).bfloat16()
+    out = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, 512, device=dev)
+    L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), B, N, H, hd ** -0.5, L.stream_ptr())
+    dO = torch.randn(B, N, C, device=dev).bfloat16()
+    dqkv = torch.empty(B, N, 3 * C, device=dev, dtype=torch.bfloat16)
+    ws = torch.empty(L.load().passt_attn_bwd_workspace_bytes(B, N, H), dtype=torch.uint8, device=dev)
+    tl = torch.zeros(2 * 512, dtype=torch.int64, device=dev)
+    run = lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(ws), B, N, H,
+                         hd ** -0.5, L.stream_ptr())
+    for _ in range(3):
+        run()
+    L.load().passt_attn_bwd_debug_timeline(L.ptr(tl))
+    run()
+    torch.cuda.synchronize()
+    L.load().passt_attn_bwd_debug_timeline(None)
+    t = tl.cpu().tolist()
+    cp, mm = t[0:512], t[512:1024]
+    t0 = min(x for x in cp + mm if x > 0)
+    rows = []
+    for k in range(12):
+        rows.append(dict(step=k, compute=[x - t0 if x else None for x in cp[k * 6:k * 6 + 6]],
+                         mma=[x - t0 if x else None for x in mm[k * 4:k * 4 + 4]]))
+    log(test="attn_bwd_timeline",
+        legend="compute: step start|sdp_full|math done|pds arrived|dq_full|dq staged ; mma: qdo_full|S,dP issued|pds_full|dV,dK,dQ issued",
         rows=rows)
 
 
