@@ -209,7 +209,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may touch
-    const int half = ew >> 2;          // which half of the BN columns this warp owns
+    const int slot = ew >> 2;          // column chunks c with c % kEpiSlots == slot belong to this warp
     uint8_t* my_epi = epi_smem + ew * 2 * Cfg::kEpiBufBytes;
     const uint32_t swz = uint32_t((lane >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= bits [7,9) of the address
     int as = 0;
@@ -226,7 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += Cfg::kColsPerChunk) {
+      for (int c0 = slot * Cfg::kColsPerChunk; c0 < BN; c0 += kEpiSlots * Cfg::kColsPerChunk) {
         const int col0 = n_blk * BN + c0;
         if (!Cfg::kOutF32) {
           uint32_t ra[32];

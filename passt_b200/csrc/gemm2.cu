@@ -17,7 +17,7 @@
 
 namespace pb {
 
-constexpr int kStages2 = 6;
+constexpr int kStages2 = 5;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same object in the even CTA of the pair
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -214,7 +214,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== epilogue warps (both CTAs; each drains its own 128 rows) =====================
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int slot = ew >> 2;
     uint8_t* my_epi = epi_smem + ew * 2 * Cfg::kEpiBufBytes;
     const uint32_t swz = uint32_t((lane >> 1) & 3);
     int as = 0;
@@ -231,7 +231,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += Cfg::kColsPerChunk) {
+      for (int c0 = slot * Cfg::kColsPerChunk; c0 < BN; c0 += kEpiSlots * Cfg::kColsPerChunk) {
         const int col0 = n_blk * BN + c0;
         if (!Cfg::kOutF32) {
           uint32_t ra[32];

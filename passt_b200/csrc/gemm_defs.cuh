@@ -14,9 +14,10 @@ enum GemmMode : int {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quadrant, each owning half of the N columns
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 12;                      // 3 per TMEM lane quadrant; column chunks are dealt round-robin
+constexpr int kEpiSlots = kEpiWarps / 4;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // warp 0 TMA, warp 1 MMA, warps 2..13 epilogue
 
 struct GemmParams {
   int M, N, K;             // D is [M,N]; K = contraction length

@@ -117,10 +117,21 @@ def _gemm(A, Bm, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, mod
 
 
 def _wgrad_splits(M_out: int, N_out: int, tokens: int) -> int:
-    tiles = (M_out // 128) * (N_out // 256)
+    """Split-K factor for the weight-gradient GEMM (2-CTA kernel: 256x256 cluster tiles over 74 clusters).
+    Minimises rounds x (k-blocks per split + epilogue cost): enough items to fill the chip in whole waves, few enough
+    that the fp32 reduce-add epilogue (one full tile per split) stays amortised."""
+    tiles = ((M_out + 255) // 256) * (N_out // 256)
     kb = (tokens + 63) // 64
-    s = max(1, min(kb, (4 * 148 + tiles - 1) // tiles))
-    return s
+    clusters, epi = 74, 8
+    best, best_cost = 1, None
+    for s in range(1, min(kb, 48) + 1):
+        per = (kb + s - 1) // s
+        s_eff = (kb + per - 1) // per          # the kernel drops empty splits
+        rounds = (tiles * s_eff + clusters - 1) // clusters
+        cost = rounds * (per + epi)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s_eff, cost
+    return best
 
 
 PARAM_ORDER_HEAD = ["cls_token", "dist_token", "new_pos_embed", "freq_new_pos_embed", "time_new_pos_embed",
