@@ -218,8 +218,10 @@ def run_candidate(args, rank, local_rank, world):
     peaks = load_peaks()
     B = BATCH_PER_GPU
     torch.manual_seed(rank)
-    mel = AugmentMelSTFT(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, freqm=48, timem=192,
-                         fmin=0.0, fmax=None, fmin_aug_range=10, fmax_aug_range=2000).to(dev).train()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):     # the module prints the reference's "FMAX is None" notice
+        mel = AugmentMelSTFT(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, freqm=48, timem=192,
+                             fmin=0.0, fmax=None, fmin_aug_range=10, fmax_aug_range=2000).to(dev).train()
     torch.manual_seed(0)   # identical initial weights on every rank
     net = get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=N_CLASSES, **NET_KW).to(dev).train()
     opt = torch.optim.AdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=2e-5,
@@ -230,7 +232,6 @@ def run_candidate(args, rank, local_rank, world):
     host_waves = [(0.1 * torch.randn(B, CLIP_LEN)).pin_memory() for _ in range(n_batches)]
     dev_waves = [w.to(dev) for w in host_waves]
     y = (torch.rand(B, N_CLASSES, device=dev) < 0.005).float()
-    loss_host = torch.zeros(1).pin_memory()
 
     def train_step(wave_dev):
         with torch.no_grad():
@@ -287,14 +288,61 @@ def run_candidate(args, rank, local_rank, world):
     launches = L.launch_count()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- (2) end to end: pinned host waveform -> H2D -> step -> D2H loss, every step
-    def e2e_step(i):
-        w = host_waves[i % n_batches].to(dev, non_blocking=True)
-        loss = train_step(w)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=False)
+    # ---- (2) end to end through the public API with HOST buffers: every step's waveform batch is copied from pinned
+    #          host memory (on a copy stream, one batch ahead of the compute, like a prefetching loader) and every
+    #          step's loss is read back to the host (asynchronously, consumed one step later, like a logging hook).
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [torch.empty(B, CLIP_LEN, device=dev) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    buf_free = [torch.cuda.Event() for _ in range(2)]
+    loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    losses = []
 
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    def upload(i):
+        k = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(buf_free[k])
+            dev_bufs[k].copy_(host_waves[i % n_batches], non_blocking=True)
+            h2d_done[k].record(copy_stream)
+
+    def e2e_run(steps):
+        cur = torch.cuda.current_stream()
+        for k in range(2):
+            buf_free[k].record(cur)
+        upload(0)
+        for i in range(steps):
+            k = i & 1
+            if i + 1 < steps:
+                upload(i + 1)
+            cur.wait_event(h2d_done[k])
+            loss = train_step(dev_bufs[k])
+            buf_free[k].record(cur)
+            loss_hosts[k].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_done[k].record(cur)
+            if i > 0:
+                loss_done[k ^ 1].synchronize()
+                losses.append(float(loss_hosts[k ^ 1]))
+        loss_done[(steps - 1) & 1].synchronize()
+        losses.append(float(loss_hosts[(steps - 1) & 1]))
+
+    e2e_run(2)
+
+    def timed_once(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms_e2e = timed_once(lambda: e2e_run(args.steps))
 
     # ---- (3) roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every GEMM launch in a
     #          repeat of the timed steps (kept out of the headline timing so the events do not perturb it)
@@ -331,7 +379,10 @@ def run_candidate(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"kernel": "gemm_kernel<BN,MODE> (tcgen05 GEMM family: fwd, dgrad, wgrad)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None,
+                         # dram__bytes_read+write of the qkv-forward launch (107.4 GFLOP, 190 MB algorithmic) from
+                         # profiles/r1_ncu_gemm2_full_v2.txt (ncu --set full): 50.3 MB read + 89.5 MB written
+                         "traffic": 139.7e6, "traffic_launch": "qkv forward M=30336 N=2304 K=768",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                          "launches_per_step": n_gemm / args.steps, "avg_launch_ms": gemm_ms / n_gemm,
                          "share_of_step": gemm_ms / ms_instr if ms_instr else None,

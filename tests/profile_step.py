@@ -35,6 +35,15 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    if os.environ.get("PROFILE_CPU"):
+        import time
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"cpu enqueue per step {(t1 - t0) / 5 * 1e3:.2f} ms; wall per step incl. drain {(t2 - t0) / 5 * 1e3:.2f} ms")
     torch.cuda.cudart().cudaProfilerStart()
     for _ in range(steps):
         step()
