@@ -24,6 +24,8 @@ size_t passt_mel_workspace_bytes(void);
 int passt_mel_init(void* workspace, int win_length, void* stream);
 /* kaldi triangular filterbank for (fmin, fmax) built ON DEVICE (preprocess.py:71-74; torchaudio kaldi.py:436-511) */
 int passt_mel_set_band(void* workspace, double fmin, double fmax, int sample_rate, void* stream);
+/* same, (fmin, fmax) read from device memory (double[2]) when the kernel runs — identical launch every step, for CUDA graphs */
+int passt_mel_set_band_dev(void* workspace, const double* band_dev, int sample_rate, void* stream);
 /* wave f32 [B,L] -> log-mel f32 [B,128,T], T = 1+(L-1)/hop.  rnd: f32 [4,B] SpecAugment uniforms or NULL (eval);
  * pre-emphasis :59, STFT :60-61, power :62, mel matmul :76, log :78, freq/time masking :80-82, affine :84 */
 int passt_mel_forward(const void* workspace, const float* wave, float* out, int B, int L, int hop, const float* rnd,
@@ -68,13 +70,14 @@ int passt_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, voi
  * optional fused spectrogram mixup (ex_audioset.py:173-177).  Patchout gathers of models/passt.py:535-552. */
 int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* patch_t, int B, int ntok, int Fm,
                  int Tm, int fstride, int tstride, const int* mix_perm, const float* mix_lam, void* stream);
-/* additive token table: conv bias + time/freq pos-embed (models/passt.py:527-529), cls/dist rows (:557-564) */
+/* additive token table: conv bias + time/freq pos-embed (models/passt.py:527-529), cls/dist rows (:557-564);
+ * toff_dev (optional int*): time-embedding offset read from device memory instead of `toff` (CUDA graphs) */
 int passt_token_table(float* tab, const float* cls, const float* dist, const float* new_pos,
                       const float* conv_bias, const float* time_pos, const float* freq_pos, const int* patch_f,
-                      const int* patch_t, int ntok, int Fg, int Tg, int toff, void* stream);
+                      const int* patch_t, int ntok, int Fg, int Tg, int toff, const int* toff_dev, void* stream);
 int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dnew_pos, float* dconv_bias,
                           float* dtime, float* dfreq, const int* patch_f, const int* patch_t, int B, int ntok,
-                          int Fg, int Tg, int toff, void* stream);
+                          int Fg, int Tg, int toff, const int* toff_dev, void* stream);
 /* f32 [R,C] -> bf16 [R,C] and bf16 [C,R] (tensor-core operand copies of the fp32 master weights) */
 int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R, int C, void* stream);
 /* final norm on cls/dist rows, (cls+dist)/2, head LayerNorm + Linear (models/passt.py:570-588, :463-464) */

@@ -24,13 +24,14 @@ _SIGS = {
     "passt_mel_workspace_bytes": (C.c_size_t, []),
     "passt_mel_init": (i32, [vp, i32, vp]),
     "passt_mel_set_band": (i32, [vp, f64, f64, i32, vp]),
+    "passt_mel_set_band_dev": (i32, [vp, vp, i32, vp]),
     "passt_mel_forward": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
     "passt_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]),
     "passt_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "passt_colsum_bf16": (i32, [vp, vp, i32, i32, i32, vp]),
     "passt_im2col": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
-    "passt_token_table": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-    "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "passt_token_table": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "passt_cast_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
     "passt_head_fwd": (i32, [vp] * 11 + [i32, i32, i32, vp]),
     "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),

@@ -56,9 +56,14 @@ __global__ void mel_tables_kernel(MelTables* t, int win_length) {
 
 // kaldi get_mel_banks (torchaudio/compliance/kaldi.py:436-511), vtln_warp_factor == 1.0 branch, fp32 like torch.
 // mel endpoints come in as doubles computed the way the python scalars are (mel_scale_scalar uses math.log).
-__global__ void mel_bank_kernel(MelBank* bank, double mel_low, double mel_high, float sample_rate) {
+__global__ void mel_bank_kernel(MelBank* bank, double mel_low, double mel_high, float sample_rate,
+                                const double* __restrict__ band_dev) {
   __shared__ float melk[kHalf];
   const int tid = threadIdx.x;
+  if (band_dev != nullptr) {   // (fmin, fmax) live in device memory (CUDA-graph replays with per-step augmentation)
+    mel_low = 1127.0 * log(1.0 + band_dev[0] / 700.0);
+    mel_high = 1127.0 * log(1.0 + band_dev[1] / 700.0);
+  }
   const float bin_width = sample_rate / float(kNfft);
   for (int k = tid; k < kHalf; k += blockDim.x) {
     const float f = __fmul_rn(bin_width, float(k));
@@ -318,7 +323,19 @@ int passt_mel_set_band(void* workspace, double fmin, double fmax, int sample_rat
   const double mel_low = 1127.0 * log(1.0 + fmin / 700.0);
   const double mel_high = 1127.0 * log(1.0 + fmax / 700.0);
   mel_bank_kernel<<<1, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(bank, mel_low, mel_high,
-                                                                         float(sample_rate));
+                                                                         float(sample_rate), nullptr);
+  PB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Same, with (fmin, fmax) read from device memory (double[2]) at kernel run time: the launch is identical every step,
+// so it can live inside a captured CUDA graph while the band augmentation still changes per step.
+int passt_mel_set_band_dev(void* workspace, const double* band_dev, int sample_rate, void* stream) {
+  using namespace pb;
+  if (!workspace || !band_dev) return PB_ERR_BAD_ARG;
+  MelBank* bank = reinterpret_cast<MelBank*>(reinterpret_cast<uint8_t*>(workspace) +
+                                             ((sizeof(MelTables) + 255) / 256) * 256);
+  mel_bank_kernel<<<1, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(bank, 0.0, 0.0, float(sample_rate), band_dev);
   PB_LAUNCH_CHECK();
   return 0;
 }

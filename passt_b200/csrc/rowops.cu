@@ -238,8 +238,10 @@ __global__ void token_table_kernel(float* __restrict__ tab, const float* __restr
                                    const float* __restrict__ dist, const float* __restrict__ new_pos,
                                    const float* __restrict__ conv_bias, const float* __restrict__ time_pos,
                                    const float* __restrict__ freq_pos, const int* __restrict__ patch_f,
-                                   const int* __restrict__ patch_t, int ntok, int Fg, int Tg, int toff) {
+                                   const int* __restrict__ patch_t, int ntok, int Fg, int Tg, int toff,
+                                   const int* __restrict__ toff_dev) {
   const int n = blockIdx.x;
+  if (toff_dev != nullptr) toff = *toff_dev;   // device-resident offset (CUDA-graph replays)
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float v;
     if (n == 0) v = cls[c] + new_pos[c];
@@ -254,8 +256,9 @@ __global__ void __launch_bounds__(192)
 token_table_bwd_kernel(const float* __restrict__ g0, float* __restrict__ dcls, float* __restrict__ ddist,
                        float* __restrict__ dnew_pos, float* __restrict__ dconv_bias, float* __restrict__ dtime,
                        float* __restrict__ dfreq, const int* __restrict__ patch_f, const int* __restrict__ patch_t,
-                       int B, int ntok, int Fg, int Tg, int toff) {
+                       int B, int ntok, int Fg, int Tg, int toff, const int* __restrict__ toff_dev) {
   const int n = blockIdx.x;
+  if (toff_dev != nullptr) toff = *toff_dev;
   const int c = threadIdx.x * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int b = 0; b < B; ++b) {
@@ -571,22 +574,22 @@ int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* 
 
 int passt_token_table(float* tab, const float* cls, const float* dist, const float* new_pos,
                       const float* conv_bias, const float* time_pos, const float* freq_pos, const int* patch_f,
-                      const int* patch_t, int ntok, int Fg, int Tg, int toff, void* stream) {
+                      const int* patch_t, int ntok, int Fg, int Tg, int toff, const int* toff_dev, void* stream) {
   using namespace pb;
   if (ntok < 2) return PB_ERR_BAD_ARG;
   token_table_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>(tab, cls, dist, new_pos, conv_bias, time_pos, freq_pos,
-                                                             patch_f, patch_t, ntok, Fg, Tg, toff);
+                                                             patch_f, patch_t, ntok, Fg, Tg, toff, toff_dev);
   PB_LAUNCH_CHECK();
   return 0;
 }
 
 int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dnew_pos, float* dconv_bias,
                           float* dtime, float* dfreq, const int* patch_f, const int* patch_t, int B, int ntok,
-                          int Fg, int Tg, int toff, void* stream) {
+                          int Fg, int Tg, int toff, const int* toff_dev, void* stream) {
   using namespace pb;
   if (ntok < 2 || B <= 0) return PB_ERR_BAD_ARG;
   token_table_bwd_kernel<<<ntok, 192, 0, (cudaStream_t)stream>>>(g0, dcls, ddist, dnew_pos, dconv_bias, dtime, dfreq,
-                                                                 patch_f, patch_t, B, ntok, Fg, Tg, toff);
+                                                                 patch_f, patch_t, B, ntok, Fg, Tg, toff, toff_dev);
   PB_LAUNCH_CHECK();
   return 0;
 }

@@ -30,13 +30,17 @@ class StepPlan:
     toffset: int
     patch_f: torch.Tensor     # int32 [ntok-2] device: freq grid row of each kept patch
     patch_t: torch.Tensor     # int32 [ntok-2] device: time grid column of each kept patch
+    toffset_dev: Optional[torch.Tensor] = None   # int32[1] device copy of toffset (graph replays read it on device)
     t_keep: Optional[torch.Tensor] = None   # CPU int64 draws (exposed for parity tests)
     f_keep: Optional[torch.Tensor] = None
     u_keep: Optional[torch.Tensor] = None
 
 
-def draw_step_plan(net, x: torch.Tensor, training: bool) -> StepPlan:
-    """Host RNG + index bookkeeping of forward_features (models/passt.py:508-553)."""
+def draw_step_plan(net, x: torch.Tensor, training: bool, static_idx: Optional[torch.Tensor] = None,
+                   static_toff: Optional[torch.Tensor] = None) -> StepPlan:
+    """Host RNG + index bookkeeping of forward_features (models/passt.py:508-553).
+    static_idx (int32 [2, ntok-2]) / static_toff (int32 [1]): device buffers to refill in place (CUDA-graph replays
+    must see the new draws at the same addresses); fresh buffers are allocated when they are None."""
     B, Cin, Fm, Tm = x.shape
     ps, (fs, ts) = net.patch_size, net.stride
     f_dim = (Fm - ps) // fs + 1                       # Conv2d output size (:315)
@@ -69,9 +73,17 @@ def draw_step_plan(net, x: torch.Tensor, training: bool) -> StepPlan:
     host = torch.stack([pf, pt]).to(torch.int32)
     if x.is_cuda:
         host = host.pin_memory()
-    dev = host.to(x.device, non_blocking=True)
+    toff_dev = None
+    if static_idx is not None:
+        static_idx.copy_(host, non_blocking=True)
+        dev = static_idx
+        if static_toff is not None:
+            static_toff.copy_(torch.tensor([toffset], dtype=torch.int32).pin_memory(), non_blocking=True)
+            toff_dev = static_toff
+    else:
+        dev = host.to(x.device, non_blocking=True)
     return StepPlan(B=B, ntok=pf.numel() + 2, Fm=Fm, Tm=Tm, toffset=toffset, patch_f=dev[0], patch_t=dev[1],
-                    t_keep=t_keep, f_keep=f_keep, u_keep=u_keep)
+                    toffset_dev=toff_dev, t_keep=t_keep, f_keep=f_keep, u_keep=u_keep)
 
 
 class WeightCache:
@@ -100,6 +112,11 @@ class WeightCache:
 
     def clear(self):
         self._store.clear()
+
+    def invalidate(self):
+        """Force a refresh on next use (parameters were updated without Python seeing it, e.g. by a graph replay)."""
+        for k, (ver, wb, wt) in list(self._store.items()):
+            self._store[k] = (None, wb, wt)
 
 
 GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
@@ -187,7 +204,8 @@ class PasstFunction(torch.autograd.Function):
         tab = torch.empty(ntok, Dm, **f32)
         L.call("passt_token_table", L.ptr(tab), L.ptr(P["cls_token"]), L.ptr(P["dist_token"]),
                L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
-               L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset, st)
+               L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset,
+               L.ptr(plan.toffset_dev), st)
         wpe, _ = wc.get(P["patch_embed.proj.weight"], False)
         xcur = torch.empty(M, Dm, **f32)
         _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
@@ -343,7 +361,7 @@ class PasstFunction(torch.autograd.Function):
         L.call("passt_token_table_bwd", L.ptr(g), L.ptr(G["cls_token"]), L.ptr(G["dist_token"]),
                L.ptr(G["new_pos_embed"]), L.ptr(G["patch_embed.proj.bias"]), L.ptr(G["time_new_pos_embed"]),
                L.ptr(G["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, Fg, Tg,
-               plan.toffset, st)
+               plan.toffset, L.ptr(plan.toffset_dev), st)
         chunk_done("cls_token", "patch_embed.proj.bias")
         net._last_flat_grad = flat
         ctx.saved = None

@@ -1,0 +1,108 @@
+"""CUDA-graph replay of one full training step (frontend -> PaSST forward -> loss -> hand-written backward ->
+optional gradient all-reduce -> optimizer), for launch-bound steps: ~300 kernel launches become one graph launch.
+
+Everything that changes from step to step is data, not launch arguments:
+  * the waveform batch and targets are copied into static device buffers,
+  * the host-side random draws the reference makes (mel band, time-embedding offset, patchout indices — same torch
+    CPU-generator calls in the same order, so indices stay bit-identical to the reference for a seed) are written
+    into small static device buffers that the kernels read (passt_mel_set_band_dev, token_table toff_dev),
+  * SpecAugment uniforms come from torch.rand inside the capture (graph-safe Philox offsets).
+
+    step = GraphedTrainStep(mel, net, optimizer, loss_fn, example_wave, example_target)
+    loss = step(wave, target)            # wave/target: device or pinned-host tensors of the example's shape
+
+The optimizer must be created with ``capturable=True``.  Parity with the eager step: tests/test_gpu_graphed.py.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import engine
+
+
+class GraphedTrainStep:
+    def __init__(self, mel, net, optimizer, loss_fn: Callable, example_wave: torch.Tensor,
+                 example_target: torch.Tensor, reducer=None, warmup: int = 3):
+        if not example_wave.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors (sm_100a); there is no CPU path")
+        self.mel, self.net, self.opt, self.loss_fn, self.reducer = mel, net, optimizer, loss_fn, reducer
+        dev = example_wave.device
+        self.wave = torch.empty_like(example_wave)
+        self.target = torch.empty_like(example_target)
+        self.band_dev = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.band_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.toff_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        mel.train(); net.train()
+        B, Lw = example_wave.shape
+        T = 1 + (Lw - 1) // mel.hopsize
+        self._x_shape = (B, 1, mel.n_mels, T)
+        # static index buffer sized from one trial plan
+        probe = engine.draw_step_plan(net, torch.empty(self._x_shape, device=dev), True)
+        self.idx_dev = torch.zeros(2, probe.ntok - 2, dtype=torch.int32, device=dev)
+        self.graph = None
+        self.loss = None
+        # eager warm-up on a side stream (allocator, cudaFuncSetAttribute, bf16 weight cache, optimizer state)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.wave.copy_(example_wave); self.target.copy_(example_target)
+            for _ in range(max(1, warmup)):
+                self._host_draws()
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._host_draws()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        torch.cuda.synchronize()
+
+    # host RNG, in the reference's order: mel band first (preprocess.py:63-64), then the network's draws
+    def _host_draws(self):
+        fmin, fmax = self.mel.draw_band()
+        self.band_host[0] = float(fmin); self.band_host[1] = float(fmax)
+        self.band_dev.copy_(self.band_host, non_blocking=True)
+        x_meta = torch.empty(self._x_shape, device="meta")
+        plan = engine.draw_step_plan(self.net, _ShapeOnCuda(x_meta, self.wave.device), True, static_idx=self.idx_dev,
+                                     static_toff=self.toff_dev)
+        self._plan = plan
+        self._band = (fmin, fmax)
+
+    def _body(self):
+        self.mel._band_dev = self.band_dev
+        self.net._preset_plan = self._plan
+        try:
+            with torch.no_grad():
+                spec = self.mel(self.wave, band=self._band).unsqueeze(1)
+            logits, _ = self.net(spec)
+            loss = self.loss_fn(logits, self.target)
+            self.opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if self.reducer is not None:
+                self.reducer.all_reduce()
+            self.opt.step()
+        finally:
+            self.mel._band_dev = None
+            self.net._preset_plan = None
+        return loss
+
+    def __call__(self, wave: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None):
+        if wave is not None:
+            self.wave.copy_(wave, non_blocking=True)
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        self._host_draws()
+        self.graph.replay()
+        self.net._wcache.invalidate()     # the replay updated the parameters behind Python's version counters
+        return self.loss
+
+
+class _ShapeOnCuda:
+    """draw_step_plan only needs the input's shape and device."""
+
+    def __init__(self, meta, device):
+        self.shape = meta.shape
+        self.device = device
+        self.is_cuda = True

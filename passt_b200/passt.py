@@ -157,6 +157,7 @@ class PaSST(nn.Module):
         self.default_cfg = {}
         self._wcache = engine.WeightCache()
         self._mix = None          # optional (perm[B] int32, lam[B] f32) set by fused_mixup()
+        self._preset_plan = None  # optional StepPlan prepared by the caller (CUDA-graph replays)
         self.last_plan = None     # StepPlan of the most recent forward (parity tests read the indices)
         self.init_weights()
 
@@ -198,7 +199,7 @@ class PaSST(nn.Module):
         for k, v in self.__dict__.items():
             if k == "_wcache":
                 new.__dict__[k] = engine.WeightCache()
-            elif k in ("last_plan", "_mix"):
+            elif k in ("last_plan", "_mix", "_preset_plan"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -231,7 +232,7 @@ class PaSST(nn.Module):
         if t_dim >= Tg and t_dim > Tg:
             warnings.warn(f"the patches time dim {t_dim} is larger than the expected time encodings {Tg}, x will be cut")
         with torch.cuda.device(x.device):
-            plan = engine.draw_step_plan(self, x, self.training)
+            plan = self._preset_plan if self._preset_plan is not None else engine.draw_step_plan(self, x, self.training)
             self.last_plan = plan
             mix, self._mix = self._mix, None
             logits, feats = engine.PasstFunction.apply(x, self, plan, mix, *self._ordered_params())

@@ -47,6 +47,7 @@ class AugmentMelSTFT(nn.Module):
         self.freqm = int(freqm)
         self.timem = int(timem)
         self._ws = {}          # device -> (workspace tensor, last (fmin, fmax))
+        self._band_dev = None   # optional float64[2] device buffer: graph replays read (fmin, fmax) from it
         self.last_draws = None  # (fmin, fmax, rnd[4,B] or None) of the most recent call, for parity tests
 
     def _workspace(self, device):
@@ -60,7 +61,17 @@ class AugmentMelSTFT(nn.Module):
             self._ws[key] = ent
         return ent
 
-    def forward(self, x):
+    def draw_band(self):
+        """The two CPU-generator draws of the reference forward (models/preprocess.py:63-68) -> (fmin, fmax)."""
+        r0 = torch.randint(self.fmin_aug_range, (1,)).item()
+        r1 = torch.randint(self.fmax_aug_range, (1,)).item()
+        if self.training:
+            return self.fmin + r0, self.fmax + self.fmax_aug_range // 2 - r1
+        return self.fmin, self.fmax
+
+    def forward(self, x, band=None):
+        """band: optional (fmin, fmax) drawn by the caller with draw_band() (CUDA-graph replays draw on the host and
+        pass the values through a device buffer); None = draw here, like the reference."""
         if not x.is_cuda:
             raise RuntimeError("passt_b200.AugmentMelSTFT runs on CUDA (sm_100a) only; there is no CPU path")
         if x.dim() != 2:
@@ -71,13 +82,7 @@ class AugmentMelSTFT(nn.Module):
         x = x.contiguous()
         B, Lw = x.shape
         # draw order of the reference: two CPU randints first (also consumed in eval)
-        r0 = torch.randint(self.fmin_aug_range, (1,)).item()
-        r1 = torch.randint(self.fmax_aug_range, (1,)).item()
-        if self.training:
-            fmin = self.fmin + r0
-            fmax = self.fmax + self.fmax_aug_range // 2 - r1
-        else:
-            fmin, fmax = self.fmin, self.fmax
+        fmin, fmax = band if band is not None else self.draw_band()
         rnd = None
         freqm = timem = 0
         if self.training and (self.freqm > 0 or self.timem > 0):
@@ -99,7 +104,11 @@ class AugmentMelSTFT(nn.Module):
         with torch.cuda.device(x.device):
             ent = self._workspace(x.device)
             st = L.stream_ptr()
-            if ent[1] != (fmin, fmax):
+            if self._band_dev is not None:
+                # graph mode: identical launch every step, the band comes from device memory
+                L.call("passt_mel_set_band_dev", L.ptr(ent[0]), L.ptr(self._band_dev), int(self.sr), st)
+                ent[1] = None
+            elif ent[1] != (fmin, fmax):
                 L.call("passt_mel_set_band", L.ptr(ent[0]), float(fmin), float(fmax), int(self.sr), st)
                 ent[1] = (fmin, fmax)
             T = 1 + (Lw - 1) // self.hopsize

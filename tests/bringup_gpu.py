@@ -232,7 +232,7 @@ def g_rowops():
     cb = torch.randn(Dm, device=dev); tp = torch.randn(Dm, 99, device=dev); fp = torch.randn(Dm, 12, device=dev)
     tab = torch.empty(ntok, Dm, device=dev)
     L.call("passt_token_table", L.ptr(tab), L.ptr(cls), L.ptr(dist), L.ptr(npos), L.ptr(cb), L.ptr(tp), L.ptr(fp),
-           L.ptr(pf), L.ptr(pt), ntok, 12, 99, 0, L.stream_ptr())
+           L.ptr(pf), L.ptr(pt), ntok, 12, 99, 0, None, L.stream_ptr())
     reft = torch.empty(ntok, Dm, device=dev)
     reft[0] = cls + npos[0]; reft[1] = dist + npos[1]
     for n in range(2, ntok):
@@ -242,7 +242,7 @@ def g_rowops():
     outs = [torch.zeros(Dm, device=dev), torch.zeros(Dm, device=dev), torch.zeros(2, Dm, device=dev),
             torch.zeros(Dm, device=dev), torch.zeros(Dm, 99, device=dev), torch.zeros(Dm, 12, device=dev)]
     L.call("passt_token_table_bwd", L.ptr(g0), *[L.ptr(o) for o in outs], L.ptr(pf), L.ptr(pt), B, ntok, 12, 99, 0,
-           L.stream_ptr())
+           None, L.stream_ptr())
     s = g0.sum(0)
     rt = torch.zeros(Dm, 99, device=dev); rf = torch.zeros(Dm, 12, device=dev)
     for n in range(2, ntok):
