@@ -53,8 +53,9 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
 void passt_attn_debug_timeline(void* buf);
 void passt_attn_bwd_debug_timeline(void* buf);
 size_t passt_attn_bwd_workspace_bytes(int B, int N, int H);
+/* d_bias_qkv (optional, f32 [3*H*64]) += column sums of d_qkv: the bias gradient of the qkv Linear */
 int passt_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
-                   void* workspace, int B, int N, int H, float scale, void* stream);
+                   float* d_bias_qkv, void* workspace, int B, int N, int H, float scale, void* stream);
 
 /* ---- row kernels ------------------------------------------------------------------------------------------------ */
 /* x_out = x_in (+ delta); h = LayerNorm(x_out) (Block residual + norm1/norm2, models/passt.py:377-380) */

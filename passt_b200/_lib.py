@@ -36,7 +36,7 @@ _SIGS = {
     "passt_head_fwd": (i32, [vp] * 11 + [i32, i32, i32, vp]),
     "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),
     "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
-    "passt_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
+    "passt_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "passt_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
     "passt_attn_debug_timeline": (None, [vp]),
     "passt_attn_bwd_debug_timeline": (None, [vp]),

@@ -33,6 +33,7 @@ struct AttnBwdParams {
   const float* lse;   // [B,H,Npad] log2 domain, pad rows +inf
   const float* Dsum;  // [B,H,Npad] pad rows 0
   float* dq_acc;      // [B,N,C] fp32 accumulation of dQ over key tiles
+  float* dbias;       // [3C] qkv bias gradient (+=) or nullptr: column sums of dK / dV are folded into the epilogue
   int Npad;
   long long* timeline;  // bring-up only: clock64 stamps of CTA 0 (nullptr in production)
 };
@@ -50,6 +51,23 @@ struct AttnBwdSmem {
   static constexpr int kBars = kVec + 2048;
   static constexpr int kTotal = kBars + 256;
 };
+
+// 32 lanes x 32 values -> lane i ends up with the sum over all lanes of value i (butterfly: 31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < n / 2) {
+        const float send = up ? v[j] : v[j + n / 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+        v[j] = (up ? v[j + n / 2] : v[j]) + recv;
+      }
+    }
+  }
+  return v[0];
+}
 
 // Persistent: each CTA walks a strided list of (key tile, head, clip) items; the TMA producer prefetches the next
 // item's K/V and Q/dO tiles while the current item is still being processed.
@@ -322,6 +340,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           o.w = pack_bf16(__uint_as_float(kk[gq * 8 + 6]) * p.scale, __uint_as_float(kk[gq * 8 + 7]) * p.scale);
           *reinterpret_cast<uint4*>(sdQ + 16384 + off) = o;                          // dK tile
         }
+        if (p.dbias != nullptr) {
+          // qkv bias gradient, K and V thirds: column sums of the bf16-rounded dK / dV rows of this tile
+          const bool valid = (kv0 + r < p.N);
+          float cv[32], ck[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            cv[e] = valid ? __bfloat162float(__float2bfloat16(__uint_as_float(vv[e]))) : 0.f;
+            ck[e] = valid ? __bfloat162float(__float2bfloat16(__uint_as_float(kk[e]) * p.scale)) : 0.f;
+          }
+          const float sv = warp_colsum32(cv, lane);
+          const float sk = warp_colsum32(ck, lane);
+          atomicAdd(p.dbias + 2 * C + h * kBHd + hc * 32 + lane, sv);
+          atomicAdd(p.dbias + C + h * kBHd + hc * 32 + lane, sk);
+        }
       }
       tc_fence_before();
       fence_proxy_async();
@@ -371,19 +403,43 @@ attn_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __res
   }
 }
 
-// dqkv[:, :, 0:C] = bf16(scale * dq_acc)
+// dqkv[:, :, 0:C] = bf16(scale * dq_acc); optionally dbias[0:C] += column sums of the packed values.
+// grid (C/256, row chunks); block 256 = 32 column groups (8 columns each) x 8 rows in flight
 __global__ void __launch_bounds__(256)
-attn_dq_pack_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int C, float scale) {
-  const size_t idx = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-  if (idx >= rows * C) return;
-  const size_t row = idx / C;
-  const int col = int(idx - row * C);
-  const float4 a = *reinterpret_cast<const float4*>(acc + idx);
-  const float4 c = *reinterpret_cast<const float4*>(acc + idx + 4);
-  uint4 o;
-  o.x = pack_bf16(a.x * scale, a.y * scale); o.y = pack_bf16(a.z * scale, a.w * scale);
-  o.z = pack_bf16(c.x * scale, c.y * scale); o.w = pack_bf16(c.z * scale, c.w * scale);
-  *reinterpret_cast<uint4*>(dqkv + row * size_t(3 * C) + col) = o;
+attn_dq_pack_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
+                    int rows, int C, float scale, int rows_per_cta) {
+  __shared__ float red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float cs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+  for (int r = r0 + rl; r < r1; r += 8) {
+    const float* src = acc + size_t(r) * C + col;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 c = *reinterpret_cast<const float4*>(src + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x * scale, a.y * scale); o.y = pack_bf16(a.z * scale, a.w * scale);
+    o.z = pack_bf16(c.x * scale, c.y * scale); o.w = pack_bf16(c.z * scale, c.w * scale);
+    *reinterpret_cast<uint4*>(dqkv + size_t(r) * (3 * C) + col) = o;
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      cs[2 * j] += __low2float(h2);
+      cs[2 * j + 1] += __high2float(h2);
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[rl][cg * 8 + e] = cs[e];
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(dbias + blockIdx.x * 256 + threadIdx.x, t);
+  }
 }
 
 }  // namespace pb
@@ -398,9 +454,9 @@ size_t passt_attn_bwd_workspace_bytes(int B, int N, int H) {
 }
 
 // qkv bf16 [B,N,3C], o bf16 [B,N,C], dO bf16 [B,N,C], lse fp32 [B,H,Npad] (log2 domain, from passt_attn_fwd)
-// -> dqkv bf16 [B,N,3C]
-int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, void* workspace,
-                   int B, int N, int H, float scale, void* stream) {
+// -> dqkv bf16 [B,N,3C]; dbias_qkv (optional, fp32 [3C]) += column sums of dqkv (the qkv Linear's bias gradient)
+int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, float* dbias_qkv,
+                   void* workspace, int B, int N, int H, float scale, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0 || !workspace) return PB_ERR_BAD_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -436,6 +492,7 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   p.total_items = B * H * p.n_kvt;
   p.Npad = p.n_kvt * kTile;
   p.dq_acc = dq_acc;
+  p.dbias = dbias_qkv;
   p.timeline = pb::g_attn_bwd_timeline;
   static bool attr_set = false;
   if (!attr_set) {
@@ -447,9 +504,15 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tmQKV, tmdO, tmdQKV, tmdQacc, p);
   PB_LAUNCH_CHECK();
   {
-    const size_t total = size_t(B) * N * C;
-    attn_dq_pack_kernel<<<unsigned((total / 8 + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv,
-                                                                          size_t(B) * N, C, scale);
+    if (C % 256 != 0) return PB_ERR_BAD_ARG;
+    const int rows = B * N;
+    const int col_blocks = C / 256;
+    int row_blocks = (kNumSMs * 4 + col_blocks - 1) / col_blocks;
+    int rows_per_cta = (rows + row_blocks - 1) / row_blocks;
+    if (rows_per_cta < 8) rows_per_cta = 8;
+    row_blocks = (rows + rows_per_cta - 1) / rows_per_cta;
+    attn_dq_pack_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, dbias_qkv, rows, C,
+                                                                      scale, rows_per_cta);
     PB_LAUNCH_CHECK();
   }
   return 0;

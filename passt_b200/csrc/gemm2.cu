@@ -176,6 +176,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, Cfg::kWgrad ? 1 : 0, Cfg::kWgrad ? 1 : 0);
+      const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_a, p.sbo_a);
+      const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(smem) + Cfg::kABytes, p.lbo_b, p.sbo_b);
+      const uint32_t kstep_a16 = p.kstep_a >> 4, kstep_b16 = p.kstep_b >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -190,15 +193,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t sb = sa + Cfg::kABytes;
+          // descriptors: warp-uniform base (per stage) + per-k offset in 16-byte units; an elected lane only issues
+          const uint64_t da0 = desc_a0 + uint64_t(uint32_t(stage) * (Cfg::kStageBytes >> 4));
+          const uint64_t db0 = desc_b0 + uint64_t(uint32_t(stage) * (Cfg::kStageBytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = make_smem_desc_sw128(sa + k * p.kstep_a, p.lbo_a, p.sbo_a);
-              const uint64_t db = make_smem_desc_sw128(sb + k * p.kstep_b, p.lbo_b, p.sbo_b);
-              umma_bf16_ss_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_2cta(tmem_d, da0 + uint64_t(k * kstep_a16), db0 + uint64_t(k * kstep_b16), idesc,
+                                (kb > kb0 || k > 0) ? 1u : 0u);
             tc_commit_2cta_mc(&empty_bar[stage]);
             if (kb == kb1 - 1) tc_commit_2cta_mc(&tfull_bar[as]);
           }

@@ -99,6 +99,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
     const float mu = mean[r], rs = rstd[r];
     float xh[kVec * 4], dy[kVec * 4];
     float sa = 0.f, sb = 0.f;
+    // issue the residual-gradient loads up front so they are in flight during the two row reductions
+    float4 gi[kVec];
+    if (g_in) {
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) gi[i] = *reinterpret_cast<const float4*>(g_in + off + i * 128 + lane * 4);
+    }
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       const int c = i * 128 + lane * 4;
@@ -131,10 +137,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = rs * (dy[4 * i + e] - sb - xh[4 * i + e] * sa);
-      if (g_in) {
-        const float4 gi = *reinterpret_cast<const float4*>(g_in + off + c);
-        o[0] += gi.x; o[1] += gi.y; o[2] += gi.z; o[3] += gi.w;
-      }
+      if (g_in) { o[0] += gi[i].x; o[1] += gi[i].y; o[2] += gi[i].z; o[3] += gi[i].w; }
       if (g_out) *reinterpret_cast<float4*>(g_out + off + c) = make_float4(o[0], o[1], o[2], o[3]);
       float4* a_c = reinterpret_cast<float4*>(acc + 2 * D + c);
       float4 ac = *a_c;

@@ -343,11 +343,10 @@ class PasstFunction(torch.autograd.Function):
             _gemm(gb, S["att"], G[pre + "attn.proj.weight"], M=Dm, N=Dm, K=M, lda=Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(Dm, Dm, M))
             L.call("passt_attn_bwd", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
-                   L.ptr(attn_ws), B, ntok, H, scale, st)
+                   L.ptr(G[pre + "attn.qkv.bias"]), L.ptr(attn_ws), B, ntok, H, scale, st)   # + qkv bias gradient
             _gemm(dqkv, wqkv_t, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=3 * Dm, ldc=Dm, mode=0)
             _gemm(dqkv, S["h1"], G[pre + "attn.qkv.weight"], M=3 * Dm, N=Dm, K=M, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(3 * Dm, Dm, M))
-            L.call("passt_colsum_bf16", L.ptr(dqkv), L.ptr(G[pre + "attn.qkv.bias"]), M, 3 * Dm, 3 * Dm, st)
             prev_bias = G[f"blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else None
             L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_in"]), L.ptr(S["mean1"]), L.ptr(S["rstd1"]),
                    L.ptr(P[pre + "norm1.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm1.weight"]),

@@ -310,10 +310,11 @@ def g_attn():
         dqkv = torch.full((B, N, 3 * C), float("nan"), device=dev, dtype=torch.bfloat16)
         wsb = L.load().passt_attn_bwd_workspace_bytes(B, N, H)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(ws), B, N, H, scale,
-               L.stream_ptr())
+        dbias = torch.zeros(3 * C, device=dev)
+        L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(dbias), L.ptr(ws), B, N,
+               H, scale, L.stream_ptr())
         torch.cuda.synchronize()
-        rec = dict(test="attn_bwd", B=B, N=N)
+        rec = dict(test="attn_bwd", B=B, N=N, dbias=relerr(dbias, dqkv.float().sum((0, 1))))
         if B <= 2:
             ref.backward(dO.float())
             g = dqkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
@@ -321,7 +322,7 @@ def g_attn():
                        nan=int(torch.isnan(dqkv.float()).sum()))
         else:
             ms = timeit(lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv),
-                                       L.ptr(ws), B, N, H, scale, L.stream_ptr()))
+                                       L.ptr(dbias), L.ptr(ws), B, N, H, scale, L.stream_ptr()))
             rec.update(ms=ms, tflops=10.0 * B * H * N * N * hd / ms / 1e9)
         log(**rec)
 
@@ -424,8 +425,8 @@ def g_attn_bwd_timeline():
     dqkv = torch.empty(B, N, 3 * C, device=dev, dtype=torch.bfloat16)
     ws = torch.empty(L.load().passt_attn_bwd_workspace_bytes(B, N, H), dtype=torch.uint8, device=dev)
     tl = torch.zeros(2 * 512, dtype=torch.int64, device=dev)
-    run = lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(ws), B, N, H,
-                         hd ** -0.5, L.stream_ptr())
+    run = lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), None, L.ptr(ws), B,
+                         N, H, hd ** -0.5, L.stream_ptr())
     for _ in range(3):
         run()
     L.load().passt_attn_bwd_debug_timeline(L.ptr(tl))

@@ -59,9 +59,13 @@ def test_graphed_step_matches_eager():
     # reduce-adds in the gradient kernels, which AdamW's sign-like update amplifies slightly
     assert losses_a[0] == losses_b[0]
     assert losses_a == pytest.approx(losses_b, rel=2e-3), (losses_a, losses_b)
+    # AdamW's update is ~lr*sign(g) in the first steps, so elements whose gradient is ~0 may move in opposite
+    # directions under a different fp32 summation order: bound = 2*lr*steps per element, and the bulk must agree
+    lr, nsteps = 1e-3, len(waves)
     for (ka, pa), (kb, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
-        frac_off = ((pa - pb).abs() > 1e-3).float().mean().item()
-        assert frac_off < 0.01, (ka, frac_off)
+        diff = (pa - pb).abs()
+        assert diff.max().item() <= 2 * lr * nsteps * 1.05, (ka, diff.max().item())
+        assert diff.mean().item() < 0.25 * lr, (ka, diff.mean().item())
     # eager inference after graph training sees the updated weights (bf16 cache invalidated)
     net_a.eval(); net_b.eval()
     with torch.no_grad():
