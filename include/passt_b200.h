@@ -33,9 +33,10 @@ int passt_mel_forward(const void* workspace, const float* wave, float* out, int 
 
 /* ---- tcgen05 GEMM family: nn.Linear fwd/bwd (models/passt.py:279-289, :338-359) and PatchEmbed.proj (:315) ---- */
 /* mode 0: C[M,N] = bf16(A[M,K] B[N,K]^T + bias)            (A,B,C bf16; K-major operands)
- * mode 1: C = bf16(acc + bias), C2 = bf16(gelu(acc + bias)) (Mlp.fc1 + nn.GELU, :285-286)
+ * mode 1: C = bf16(gelu'(acc + bias)), C2 = bf16(gelu(acc + bias)) (Mlp.fc1 + nn.GELU, :285-286; exact erf)
  * mode 2: C f32 = acc + aux_f32[row % aux_period, :]        (patch-embed: bias + pos-embeds + cls/dist rows)
- * mode 3: C = bf16(acc * gelu'(aux_bf16[row, :]))           (fc2 dgrad fused with GELU backward)
+ * mode 3: C = bf16(acc * aux_bf16[row, :]) with aux = gelu'(pre) saved by mode 1 (fc2 dgrad fused with GELU
+ *         backward); if `bias` is non-NULL it is an OUTPUT: bias[n] += sum_m C[m,n] (the fc1 bias gradient)
  * mode 4: C f32 [M,N] += A[K,M]^T B[K,N]                    (weight gradient; split-K, TMA reduce-add)      */
 int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                     int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,

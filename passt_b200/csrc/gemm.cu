@@ -90,7 +90,7 @@ struct GemmCfg {
   static constexpr int kEpiBufBytes = 32 * 64;                       // 32 rows x 64 B (SWIZZLE_64B boxes)
   static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;     // 2 buffers per epilogue warp
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + align slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 2048 + 1024;  // + colsum table + align slack
   static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;           // one 64-byte output row segment
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
@@ -109,6 +109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN] (mode 3 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +129,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     fence_barrier_init();
   }
+  if (MODE == kGeluGradBf16)
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_colsum[i] = 0.f;
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_holder);
   tc_fence_before();
   __syncthreads();
@@ -216,6 +219,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
+    int tile_parity = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int split = t / (p.m_tiles * p.n_tiles);
       const int tt = t - split * (p.m_tiles * p.n_tiles);
@@ -260,6 +264,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   v[i * 8 + 2 * j + 1] *= __high2float(h2);
                 }
               }
+            }
+            if (p.bias != nullptr) {
+              // bias gradient of the layer that produced `pre`: column sums of this 32x32 block (rows >= M are 0)
+              float cs[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) cs[i] = v[i];
+              const float t = warp_colsum32(cs, lane);
+              atomicAdd(&s_colsum[(tile_parity << 8) + c0 + lane], t);
             }
           }
           float w2[32];
@@ -348,6 +360,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           buf ^= 1;
         }
+      }
+      if (MODE == kGeluGradBf16 && p.bias != nullptr) {
+        named_bar_sync(2, kEpiWarps * 32);
+        const int et = threadIdx.x - 64;
+        if (et < BN) {
+          float* slot = &s_colsum[(tile_parity << 8) + et];
+          atomicAdd(const_cast<float*>(p.bias) + n_blk * BN + et, *slot);
+          *slot = 0.f;
+        }
+        tile_parity ^= 1;
       }
       // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above) -> hand it back
       tc_fence_before();

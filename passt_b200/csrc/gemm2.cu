@@ -85,7 +85,7 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufBytes = 32 * 64;
   static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
-  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 2048 + 1024;
   static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
@@ -106,6 +106,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull_bar = bars + 2 * kStages2;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN] (mode 3 only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +128,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     fence_barrier_init();
   }
+  if (MODE == kGeluGradBf16)
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_colsum[i] = 0.f;
   if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_holder);
   tc_fence_before();
   cluster_sync_all();
@@ -222,6 +225,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
+    int tile_parity = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int split = t / (p.m_tiles * p.n_tiles);
       const int tt = t - split * (p.m_tiles * p.n_tiles);
@@ -266,6 +270,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   v[i * 8 + 2 * j + 1] *= __high2float(h2);
                 }
               }
+            }
+            if (p.bias != nullptr) {
+              // bias gradient of the layer that produced `pre`: column sums of this 32x32 block (rows >= M are 0)
+              float cs[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) cs[i] = v[i];
+              const float t = warp_colsum32(cs, lane);
+              atomicAdd(&s_colsum[(tile_parity << 8) + c0 + lane], t);
             }
           }
           float w2[32];
@@ -353,6 +365,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           buf ^= 1;
         }
+      }
+      if (MODE == kGeluGradBf16 && p.bias != nullptr) {
+        // all 12 epilogue warps have added their blocks: flush this tile's 256 column sums, re-zero the buffer
+        named_bar_sync(2, kEpiWarps * 32);
+        const int et = threadIdx.x - 64;
+        if (et < BN) {
+          float* slot = &s_colsum[(tile_parity << 8) + et];
+          atomicAdd(const_cast<float*>(p.bias) + n_blk * BN + et, *slot);
+          *slot = 0.f;
+        }
+        tile_parity ^= 1;
       }
       tc_fence_before();
       __syncwarp();

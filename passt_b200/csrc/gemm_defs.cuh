@@ -24,7 +24,7 @@ struct GemmParams {
   int m_tiles, n_tiles;    // tile grid
   int k_blocks;            // total BK blocks along K
   int splits;              // split-K factor (1 for TN modes)
-  const float* bias;       // [N] or nullptr
+  const float* bias;       // [N] or nullptr.  mode 3: OUTPUT (float*), += column sums of C (bias gradient) if non-null
   const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 gelu'(pre) [M, ld_aux]
   int aux_period;          // mode 2
   int ld_aux;              // elements
@@ -59,6 +59,23 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
   dg = fmaf(x * e, 0.3989422804014327f, cdf);
 }
 
+
+// 32 lanes x 32 values -> lane i ends up with the sum over all lanes of value i (butterfly: 31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < n / 2) {
+        const float send = up ? v[j] : v[j + n / 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+        v[j] = (up ? v[j + n / 2] : v[j]) + recv;
+      }
+    }
+  }
+  return v[0];
+}
 
 struct DescOverride {
   int active = 0;

@@ -87,31 +87,40 @@ def draw_step_plan(net, x: torch.Tensor, training: bool, static_idx: Optional[to
 
 
 class WeightCache:
-    """bf16 copies of the fp32 master weights: W [out,in] for fwd/wgrad and W^T [in,out] for dgrad.
-    Refreshed by one cast_transpose kernel per matrix whenever the parameter changed (optimizer step)."""
+    """bf16 copies of the fp32 master weights: W [out,in] for fwd/wgrad and W^T [in,out] for dgrad, refreshed by one
+    cast_transpose kernel per matrix.
+
+    Staleness cannot be detected from ``Tensor._version``: fused CUDA optimizers (torch.optim.AdamW(fused=True))
+    and CUDA-graph replays update parameters without bumping it.  Policy: every *training* forward refreshes
+    unconditionally (``force=True``; 49 small kernels, ~0.1 ms) and marks the cache dirty; the next no-grad forward
+    refreshes once more (the optimizer ran after the last training forward) and clears the flag.  In-place edits
+    that do bump the version (load_state_dict, SWA averaging, manual ``p.data`` changes via ops) are caught by the
+    version check as well."""
 
     def __init__(self):
-        self._store: Dict[int, tuple] = {}
+        self._store: Dict[tuple, tuple] = {}
+        self.dirty = False
 
-    def get(self, p: torch.Tensor, need_t: bool):
+    def get(self, p: torch.Tensor, need_t: bool, force: bool = False):
         key = (p.data_ptr(), tuple(p.shape))
         ent = self._store.get(key)
         ver = (p.data_ptr(), p._version)
-        if ent is not None and ent[0] == ver and (ent[2] is not None or not need_t):
+        if (not force and ent is not None and ent[0] == ver and (ent[2] is not None or not need_t)):
             return ent[1], ent[2]
         w2 = p.detach().reshape(p.shape[0], -1)
         R, C = w2.shape
         wb = ent[1] if ent is not None and ent[1].device == p.device else torch.empty(R, C, dtype=BF16, device=p.device)
-        wt = None
-        if need_t:
-            wt = ent[2] if ent is not None and ent[2] is not None and ent[2].device == p.device else \
-                torch.empty(C, R, dtype=BF16, device=p.device)
+        wt = ent[2] if ent is not None and ent[2] is not None and ent[2].device == p.device else None
+        if need_t and wt is None:
+            wt = torch.empty(C, R, dtype=BF16, device=p.device)
+        # an existing transposed copy is always kept and refreshed too: a captured CUDA graph may hold its address
         L.call("passt_cast_transpose", L.ptr(w2), L.ptr(wb), L.ptr(wt), R, C, L.stream_ptr())
         self._store[key] = (ver, wb, wt)
         return wb, wt
 
     def clear(self):
         self._store.clear()
+        self.dirty = False
 
     def invalidate(self):
         """Force a refresh on next use (parameters were updated without Python seeing it, e.g. by a graph replay)."""
@@ -184,6 +193,12 @@ class PasstFunction(torch.autograd.Function):
         fs, ts = net.stride
         need_grad = any(ctx.needs_input_grad[4:])   # Function.forward itself runs with grad mode off
         wc: WeightCache = net._wcache
+        if need_grad:
+            refresh = True          # an optimizer step may have happened since the last forward (see WeightCache)
+            wc.dirty = True
+        else:
+            refresh = wc.dirty
+            wc.dirty = False
         st = L.stream_ptr()
         x32 = x.detach()
         if x32.dtype != torch.float32:
@@ -206,7 +221,7 @@ class PasstFunction(torch.autograd.Function):
                L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
                L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset,
                L.ptr(plan.toffset_dev), st)
-        wpe, _ = wc.get(P["patch_embed.proj.weight"], False)
+        wpe, _ = wc.get(P["patch_embed.proj.weight"], False, refresh)
         xcur = torch.empty(M, Dm, **f32)
         _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
 
@@ -215,10 +230,10 @@ class PasstFunction(torch.autograd.Function):
         scale = float((Dm // H) ** -0.5)
         for i in range(depth):
             pre = f"blocks.{i}."
-            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], need_grad)
-            wproj, _ = wc.get(P[pre + "attn.proj.weight"], need_grad)
-            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], need_grad)
-            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], need_grad)
+            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], need_grad, refresh)
+            wproj, _ = wc.get(P[pre + "attn.proj.weight"], need_grad, refresh)
+            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], need_grad, refresh)
+            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], need_grad, refresh)
             # x_in = xcur (+ delta of the previous block); h1 = LN1(x_in)
             h1 = torch.empty(M, Dm, **b16)
             mean1 = torch.empty(M, **f32); rstd1 = torch.empty(M, **f32)
@@ -327,14 +342,13 @@ class PasstFunction(torch.autograd.Function):
             _, wfc1_t = wc.get(P[pre + "mlp.fc1.weight"], True)
             _, wfc2_t = wc.get(P[pre + "mlp.fc2.weight"], True)
             # ---- MLP
-            _gemm(gb, wfc2_t, dact, aux=S["pre_act"], M=M, N=hidden, K=Dm, lda=Dm, ldb=Dm, ldc=hidden, mode=3,
-                  ld_aux=hidden)                                           # d pre = (g W2) * gelu'(pre)
+            _gemm(gb, wfc2_t, dact, aux=S["pre_act"], bias=G[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm,
+                  ldb=Dm, ldc=hidden, mode=3, ld_aux=hidden)   # d pre = (g W2) * gelu'(pre); + fc1 bias gradient
             _gemm(gb, S["act"], G[pre + "mlp.fc2.weight"], M=Dm, N=hidden, K=M, lda=Dm, ldb=hidden, ldc=hidden,
                   mode=4, splits=_wgrad_splits(Dm, hidden, M))
             _gemm(dact, wfc1_t, dh, M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden, ldc=Dm, mode=0)
             _gemm(dact, S["h2"], G[pre + "mlp.fc1.weight"], M=hidden, N=Dm, K=M, lda=hidden, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(hidden, Dm, M))
-            L.call("passt_colsum_bf16", L.ptr(dact), L.ptr(G[pre + "mlp.fc1.bias"]), M, hidden, hidden, st)
             L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_mid"]), L.ptr(S["mean2"]), L.ptr(S["rstd2"]),
                    L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm2.weight"]),
                    L.ptr(G[pre + "norm2.bias"]), L.ptr(G[pre + "attn.proj.bias"]), M, Dm, st)

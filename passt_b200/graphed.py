@@ -95,7 +95,7 @@ class GraphedTrainStep:
             self.target.copy_(target, non_blocking=True)
         self._host_draws()
         self.graph.replay()
-        self.net._wcache.invalidate()     # the replay updated the parameters behind Python's version counters
+        self.net._wcache.dirty = True     # the replay updated the parameters: the next eager forward must re-cast
         return self.loss
 
 

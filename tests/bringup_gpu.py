@@ -109,9 +109,10 @@ def g_gemm_modes():
     # mode 3: gelu-grad
     prev = (torch.randn(M, N, device=dev)).bfloat16()
     Cb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    gemm(A, B, Cb, aux=prev, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, mode=3, ld_aux=N)
+    csum = torch.zeros(N, device=dev)
+    gemm(A, B, Cb, aux=prev, bias=csum, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, mode=3, ld_aux=N)
     torch.cuda.synchronize()
-    log(test="gemm_mode3", relerr=relerr(Cb, acc * prev.float()))
+    log(test="gemm_mode3", relerr=relerr(Cb, acc * prev.float()), colsum=relerr(csum, (acc * prev.float()).sum(0)))
 
 
 def g_gemm_wgrad():

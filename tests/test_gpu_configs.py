@@ -100,3 +100,29 @@ def test_long_clip_20s_variant():
     with torch.no_grad():
         logits, _ = net(x)
     assert logits.shape == (1, 527) and torch.isfinite(logits).all() and net.last_plan.ntok == 12 * 199 + 2
+
+
+def test_bf16_weight_cache_tracks_fused_optimizer_updates():
+    """torch.optim.AdamW(fused=True) updates parameters without bumping Tensor._version: the tensor-core weight copies
+    must still follow the fp32 masters (every training forward re-casts; the first eval forward afterwards too)."""
+    import copy
+    from passt_b200.passt import get_model, lighten_model
+    with quiet():
+        net = lighten_model(get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, s_patchout_t=40,
+                                      s_patchout_f=4), cut_depth=10).to(DEV).train()
+    opt = torch.optim.AdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=1e-2, fused=True)
+    torch.manual_seed(0)
+    x = torch.randn(4, 1, 128, 1000, device=DEV)
+    y = (torch.rand(4, 527, device=DEV) < 0.05).float()
+    for _ in range(3):
+        logits, _ = net(x)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    net.eval()
+    fresh = copy.deepcopy(net)            # deepcopy starts with an empty weight cache -> casts from the fp32 masters
+    with torch.no_grad():
+        a, _ = net(x)
+        b, _ = fresh(x)
+    assert torch.equal(a, b)
