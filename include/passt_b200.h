@@ -37,7 +37,9 @@ int passt_mel_forward(const void* workspace, const float* wave, float* out, int 
  * mode 2: C f32 = acc + aux_f32[row % aux_period, :]        (patch-embed: bias + pos-embeds + cls/dist rows)
  * mode 3: C = bf16(acc * aux_bf16[row, :]) with aux = gelu'(pre) saved by mode 1 (fc2 dgrad fused with GELU
  *         backward); if `bias` is non-NULL it is an OUTPUT: bias[n] += sum_m C[m,n] (the fc1 bias gradient)
- * mode 4: C f32 [M,N] += A[K,M]^T B[K,N]                    (weight gradient; split-K, TMA reduce-add)      */
+ * mode 4: C f32 [M,N] += A[K,M]^T B[K,N]                    (weight gradient; split-K, TMA reduce-add)
+ * mode 0|16, 3|16: same as 0 / 3 with B given as [K,N] row-major — the nn.Linear weight itself, so input
+ *         gradients need no transposed weight copy (the operand is read MN-major)                           */
 int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                     int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,
                     int max_ctas, void* stream);

@@ -80,9 +80,11 @@ int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, bool BMN = false>
 struct GemmCfg {
   static constexpr bool kWgrad = (MODE == kWgradF32);
+  static constexpr bool kAMn = kWgrad;
+  static constexpr bool kBMn = kWgrad || BMN;
   static constexpr bool kOutF32 = (MODE == kRowTabF32 || MODE == kWgradF32);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
@@ -95,11 +97,11 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
-  using Cfg = GemmCfg<BN, MODE>;
+  using Cfg = GemmCfg<BN, MODE, BMN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
@@ -156,14 +158,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (!Cfg::kWgrad) {
+          if (!Cfg::kAMn) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g)     // MN-major: boxes of [64 k rows][64 MN elements]
+              tma_load_2d(sa + g * 8192, &tmA, &full_bar[stage], m_blk * BM + g * 64, kb * BK);
+          }
+          if (!Cfg::kBMn) {
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
-            // MN-major: boxes of [64 tokens][64 MN elements]
-#pragma unroll
-            for (int g = 0; g < BM / 64; ++g)
-              tma_load_2d(sa + g * 8192, &tmA, &full_bar[stage], m_blk * BM + g * 64, kb * BK);
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g)
               tma_load_2d(sb + g * 8192, &tmB, &full_bar[stage], n_blk * BN + g * 64, kb * BK);
@@ -174,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, Cfg::kWgrad ? 1 : 0, Cfg::kWgrad ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, Cfg::kAMn ? 1 : 0, Cfg::kBMn ? 1 : 0);
     const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_a, p.sbo_a);
     const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(smem) + Cfg::kABytes, p.lbo_b, p.sbo_b);
     const uint32_t kstep_a16 = p.kstep_a >> 4, kstep_b16 = p.kstep_b >> 4;
@@ -391,29 +395,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 DescOverride g_desc_override;
 static int g_use_2cta = 1;   // passt_gemm_set_2cta(): bring-up / A-B switch between the 1-CTA and 2-CTA kernels
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool BMN = false>
 static int launch_gemm(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux,
                        int M, int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits,
                        int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, MODE>;
+  using Cfg = GemmCfg<BN, MODE, BMN>;
   if (N % BN != 0) return PB_ERR_BAD_ARG;
   if ((lda % 8) || (ldb % 8)) return PB_ERR_BAD_ARG;
   CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
-  if (!Cfg::kWgrad) {
+  if (!Cfg::kAMn) {
     if (K % 8) return PB_ERR_BAD_ARG;
     if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, uint64_t(lda) * 2, BM, BK,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
-    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, uint64_t(ldb) * 2, BN, BK,
-                           CU_TENSOR_MAP_SWIZZLE_128B)))
-      return rc;
   } else {
-    // A: [K tokens, M] row-major (M contiguous); B: [K tokens, N] row-major
     if (M % BM != 0) return PB_ERR_BAD_ARG;
     if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, uint64_t(lda) * 2, BK, 64,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
+  }
+  if (!Cfg::kBMn) {
+    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, uint64_t(ldb) * 2, BN, BK,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  } else {
     if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, uint64_t(ldb) * 2, BK, 64,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
@@ -451,23 +457,17 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
   p.aux = aux;
   p.aux_period = aux_period > 0 ? aux_period : 1;
   p.ld_aux = ld_aux;
-  if (!Cfg::kWgrad) {
-    // K-major SW128: 8-row atoms of 1024 B; K advance of 16 elements = 32 B inside the swizzle atom
-    p.lbo_a = 16; p.sbo_a = 1024; p.kstep_a = 32;
-    p.lbo_b = 16; p.sbo_b = 1024; p.kstep_b = 32;
-  } else {
-    // MN-major SW128: 64-element MN groups 8192 B apart (LBO), 8-token K groups 1024 B apart (SBO);
-    // K advance of 16 tokens = 2 K groups = 2048 B
-    p.lbo_a = 8192; p.sbo_a = 1024; p.kstep_a = 2048;
-    p.lbo_b = 8192; p.sbo_b = 1024; p.kstep_b = 2048;
-  }
+  // K-major SW128: 8-row atoms of 1024 B, K advance of 16 elements = 32 B inside the swizzle atom.
+  // MN-major SW128: 64-element MN groups 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), K advance = 2048 B.
+  if (!Cfg::kAMn) { p.lbo_a = 16; p.sbo_a = 1024; p.kstep_a = 32; } else { p.lbo_a = 8192; p.sbo_a = 1024; p.kstep_a = 2048; }
+  if (!Cfg::kBMn) { p.lbo_b = 16; p.sbo_b = 1024; p.kstep_b = 32; } else { p.lbo_b = 8192; p.sbo_b = 1024; p.kstep_b = 2048; }
   if (g_desc_override.active) {
     p.lbo_a = g_desc_override.v[0]; p.sbo_a = g_desc_override.v[1]; p.kstep_a = g_desc_override.v[2];
     p.lbo_b = g_desc_override.v[3]; p.sbo_b = g_desc_override.v[4]; p.kstep_b = g_desc_override.v[5];
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PB_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<BN, MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -475,7 +475,7 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid <= 0) return 0;
-  gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+  gemm_kernel<BN, MODE, BMN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
   PB_LAUNCH_CHECK();
   return 0;
 }
@@ -501,8 +501,16 @@ int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0 || K <= 0) return PB_ERR_BAD_ARG;
   const bool wide = (N % 256 == 0);
-  if (g_use_2cta && wide && max_ctas == 0 && (mode != kWgradF32 || M % 256 == 0) && mode >= 0 && mode <= 4)
+  if (g_use_2cta && wide && max_ctas == 0 && (mode != kWgradF32 || M % 256 == 0))
     return launch_gemm2(mode, A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, st);
+  if (mode == (kBiasBf16 | kBRowMajorKN))
+    return wide ? launch_gemm<256, kBiasBf16, true>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux,
+                                                    splits, max_ctas, st)
+                : PB_ERR_BAD_ARG;
+  if (mode == (kGeluGradBf16 | kBRowMajorKN))
+    return wide ? launch_gemm<256, kGeluGradBf16, true>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period,
+                                                        ld_aux, splits, max_ctas, st)
+                : PB_ERR_BAD_ARG;
   switch (mode) {
     case kBiasBf16:
       return wide ? launch_gemm<256, kBiasBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux,

@@ -75,10 +75,12 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-template <int MODE>
+template <int MODE, bool BMN>
 struct Gemm2Cfg {
   static constexpr int BN = 256;
   static constexpr bool kWgrad = (MODE == kWgradF32);
+  static constexpr bool kAMn = kWgrad;               // A is [K, M] row-major (MN-major operand)
+  static constexpr bool kBMn = kWgrad || BMN;        // B is [K, N] row-major (MN-major operand)
   static constexpr bool kOutF32 = (MODE == kRowTabF32 || MODE == kWgradF32);
   static constexpr int kABytes = BM * BK * 2;           // this CTA's 128 A rows
   static constexpr int kBBytes = (BN / 2) * BK * 2;     // this CTA's half of the B tile
@@ -90,11 +92,11 @@ struct Gemm2Cfg {
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
-template <int MODE>
+template <int MODE, bool BMN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
-  using Cfg = Gemm2Cfg<MODE>;
+  using Cfg = Gemm2Cfg<MODE, BMN>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   // both CTAs see the same dynamic-smem base offset, so the aligned offset is identical in the pair
@@ -160,13 +162,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // bytes of both CTAs
-          if (!Cfg::kWgrad) {
+          if (!Cfg::kAMn) {
             tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m0);
-            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n0);
           } else {
 #pragma unroll
-            for (int g = 0; g < BM / 64; ++g)
+            for (int g = 0; g < BM / 64; ++g)     // MN-major: boxes of [64 k rows][64 MN elements]
               tma_load_2d_2sm(sa + g * 8192, &tmA, &full_bar[stage], m0 + g * 64, kb * BK);
+          }
+          if (!Cfg::kBMn) {
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
 #pragma unroll
             for (int g = 0; g < (BN / 2) / 64; ++g)
               tma_load_2d_2sm(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, kb * BK);
@@ -178,7 +183,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, Cfg::kWgrad ? 1 : 0, Cfg::kWgrad ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, Cfg::kAMn ? 1 : 0, Cfg::kBMn ? 1 : 0);
       const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(smem), p.lbo_a, p.sbo_a);
       const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(smem) + Cfg::kABytes, p.lbo_b, p.sbo_b);
       const uint32_t kstep_a16 = p.kstep_a >> 4, kstep_b16 = p.kstep_b >> 4;
@@ -390,21 +395,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int MODE>
+template <int MODE, bool BMN>
 static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                           int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits,
                           cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<MODE>;
+  using Cfg = Gemm2Cfg<MODE, BMN>;
   constexpr int BN = Cfg::BN;
   if (N % BN != 0 || (lda % 8) || (ldb % 8)) return PB_ERR_BAD_ARG;
   CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
-  if (!Cfg::kWgrad) {
+  if (!Cfg::kAMn) {
     if (K % 8) return PB_ERR_BAD_ARG;
     if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, uint64_t(lda) * 2, BM, BK,
-                           CU_TENSOR_MAP_SWIZZLE_128B)))
-      return rc;
-    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, uint64_t(ldb) * 2, BN / 2, BK,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   } else {
@@ -412,6 +414,12 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
     if ((rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, uint64_t(lda) * 2, BK, 64,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
+  }
+  if (!Cfg::kBMn) {
+    if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, uint64_t(ldb) * 2, BN / 2, BK,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  } else {
     if ((rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, uint64_t(ldb) * 2, BK, 64,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
@@ -445,49 +453,43 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
     p.splits = (p.k_blocks + per - 1) / per;
   }
   p.bias = bias; p.aux = aux; p.aux_period = aux_period > 0 ? aux_period : 1; p.ld_aux = ld_aux;
-  if (!Cfg::kWgrad) {
-    p.lbo_a = 16; p.sbo_a = 1024; p.kstep_a = 32;
-    p.lbo_b = 16; p.sbo_b = 1024; p.kstep_b = 32;
-  } else {
-    p.lbo_a = 8192; p.sbo_a = 1024; p.kstep_a = 2048;
-    p.lbo_b = 8192; p.sbo_b = 1024; p.kstep_b = 2048;
-  }
+  // K-major SW128: 8-row atoms of 1024 B, K advance of 16 elements = 32 B inside the swizzle atom.
+  // MN-major SW128: 64-element MN groups 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), K advance = 2048 B.
+  if (!Cfg::kAMn) { p.lbo_a = 16; p.sbo_a = 1024; p.kstep_a = 32; } else { p.lbo_a = 8192; p.sbo_a = 1024; p.kstep_a = 2048; }
+  if (!Cfg::kBMn) { p.lbo_b = 16; p.sbo_b = 1024; p.kstep_b = 32; } else { p.lbo_b = 8192; p.sbo_b = 1024; p.kstep_b = 2048; }
   if (g_desc_override.active) {
     p.lbo_a = g_desc_override.v[0]; p.sbo_a = g_desc_override.v[1]; p.kstep_a = g_desc_override.v[2];
     p.lbo_b = g_desc_override.v[3]; p.sbo_b = g_desc_override.v[4]; p.kstep_b = g_desc_override.v[5];
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PB_CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
     attr_set = true;
   }
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
   if (clusters <= 0) return 0;
-  gemm2_kernel<MODE><<<clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+  gemm2_kernel<MODE, BMN><<<clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
   PB_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_gemm2(int mode, const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                  int N, int K, int lda, int ldb, int ldc, int aux_period, int ld_aux, int splits, cudaStream_t stream) {
+#define PB_G2(MODE_, BMN_) \
+  launch_gemm2_t<MODE_, BMN_>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream)
   switch (mode) {
-    case kBiasBf16:
-      return launch_gemm2_t<kBiasBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
-    case kBiasGeluBf16:
-      return launch_gemm2_t<kBiasGeluBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits,
-                                           stream);
-    case kRowTabF32:
-      return launch_gemm2_t<kRowTabF32>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
-    case kGeluGradBf16:
-      return launch_gemm2_t<kGeluGradBf16>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits,
-                                           stream);
-    case kWgradF32:
-      return launch_gemm2_t<kWgradF32>(A, B, C, C2, bias, aux, M, N, K, lda, ldb, ldc, aux_period, ld_aux, splits, stream);
-    default:
-      return PB_ERR_BAD_ARG;
+    case kBiasBf16: return PB_G2(kBiasBf16, false);
+    case kBiasGeluBf16: return PB_G2(kBiasGeluBf16, false);
+    case kRowTabF32: return PB_G2(kRowTabF32, false);
+    case kGeluGradBf16: return PB_G2(kGeluGradBf16, false);
+    case kWgradF32: return PB_G2(kWgradF32, false);
+    case kBiasBf16 | kBRowMajorKN: return PB_G2(kBiasBf16, true);
+    case kGeluGradBf16 | kBRowMajorKN: return PB_G2(kGeluGradBf16, true);
+    default: return PB_ERR_BAD_ARG;
   }
+#undef PB_G2
 }
 
 }  // namespace pb

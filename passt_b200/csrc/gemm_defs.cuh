@@ -10,6 +10,7 @@ enum GemmMode : int {
   kRowTabF32 = 2,     // C = fp32(acc + tab[row % period, col])
   kGeluGradBf16 = 3,  // C = bf16(acc * aux[row, col])   (aux = gelu'(pre) saved by mode 1)
   kWgradF32 = 4,      // C += fp32(acc)   (MN-major operands, split-K, TMA reduce-add)
+  kBRowMajorKN = 16,  // flag for modes 0 / 3: B is given as [K, N] row-major (the nn.Linear weight itself for dgrad)
 };
 
 constexpr int BM = 128;

@@ -313,6 +313,18 @@ cast_transpose_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ 
   }
 }
 
+// fp32 -> bf16, 8 elements per thread (no transposed copy requested)
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n8) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(in)[2 * i];
+  const float4 b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+  uint4 o;
+  o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // classifier head
 // ------------------------------------------------------------------------------------------------
@@ -600,6 +612,12 @@ int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dne
 int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R, int C, void* stream) {
   using namespace pb;
   if (R <= 0 || C <= 0) return PB_ERR_BAD_ARG;
+  if (outT_bf16 == nullptr && out_bf16 != nullptr && (size_t(R) * C) % 8 == 0) {
+    const size_t n8 = size_t(R) * C / 8;
+    cast_bf16_kernel<<<unsigned((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_bf16, n8);
+    PB_LAUNCH_CHECK();
+    return 0;
+  }
   cast_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
       in, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)outT_bf16, R, C);
   PB_LAUNCH_CHECK();

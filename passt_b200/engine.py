@@ -87,8 +87,9 @@ def draw_step_plan(net, x: torch.Tensor, training: bool, static_idx: Optional[to
 
 
 class WeightCache:
-    """bf16 copies of the fp32 master weights: W [out,in] for fwd/wgrad and W^T [in,out] for dgrad, refreshed by one
-    cast_transpose kernel per matrix.
+    """bf16 copies of the fp32 master weights W [out,in] (forward: K-major B operand; dgrad: the same bytes read as a
+    [K, N] row-major MN-major B operand; a transposed copy is only produced on request), refreshed by one cast
+    kernel per matrix.
 
     Staleness cannot be detected from ``Tensor._version``: fused CUDA optimizers (torch.optim.AdamW(fused=True))
     and CUDA-graph replays update parameters without bumping it.  Policy: every *training* forward refreshes
@@ -128,6 +129,7 @@ class WeightCache:
             self._store[k] = (None, wb, wt)
 
 
+B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMajorKN)
 GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
 
 
@@ -230,10 +232,10 @@ class PasstFunction(torch.autograd.Function):
         scale = float((Dm // H) ** -0.5)
         for i in range(depth):
             pre = f"blocks.{i}."
-            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], need_grad, refresh)
-            wproj, _ = wc.get(P[pre + "attn.proj.weight"], need_grad, refresh)
-            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], need_grad, refresh)
-            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], need_grad, refresh)
+            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], False, refresh)
+            wproj, _ = wc.get(P[pre + "attn.proj.weight"], False, refresh)
+            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], False, refresh)
+            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], False, refresh)
             # x_in = xcur (+ delta of the previous block); h1 = LN1(x_in)
             h1 = torch.empty(M, Dm, **b16)
             mean1 = torch.empty(M, **f32); rstd1 = torch.empty(M, **f32)
@@ -337,28 +339,29 @@ class PasstFunction(torch.autograd.Function):
         for i in reversed(range(depth)):
             pre = f"blocks.{i}."
             S = ctx.saved[i]
-            _, wqkv_t = wc.get(P[pre + "attn.qkv.weight"], True)
-            _, wproj_t = wc.get(P[pre + "attn.proj.weight"], True)
-            _, wfc1_t = wc.get(P[pre + "mlp.fc1.weight"], True)
-            _, wfc2_t = wc.get(P[pre + "mlp.fc2.weight"], True)
+            # dgrad GEMMs read the bf16 weight itself as a [K, N] row-major (MN-major) B operand: no transposed copies
+            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], False)
+            wproj, _ = wc.get(P[pre + "attn.proj.weight"], False)
+            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], False)
+            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], False)
             # ---- MLP
-            _gemm(gb, wfc2_t, dact, aux=S["pre_act"], bias=G[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm,
-                  ldb=Dm, ldc=hidden, mode=3, ld_aux=hidden)   # d pre = (g W2) * gelu'(pre); + fc1 bias gradient
+            _gemm(gb, wfc2, dact, aux=S["pre_act"], bias=G[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm,
+                  ldb=hidden, ldc=hidden, mode=3 | B_KN, ld_aux=hidden)   # d pre = (g W2) * gelu'(pre); + fc1 bias grad
             _gemm(gb, S["act"], G[pre + "mlp.fc2.weight"], M=Dm, N=hidden, K=M, lda=Dm, ldb=hidden, ldc=hidden,
                   mode=4, splits=_wgrad_splits(Dm, hidden, M))
-            _gemm(dact, wfc1_t, dh, M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden, ldc=Dm, mode=0)
+            _gemm(dact, wfc1, dh, M=M, N=Dm, K=hidden, lda=hidden, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(dact, S["h2"], G[pre + "mlp.fc1.weight"], M=hidden, N=Dm, K=M, lda=hidden, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(hidden, Dm, M))
             L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_mid"]), L.ptr(S["mean2"]), L.ptr(S["rstd2"]),
                    L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm2.weight"]),
                    L.ptr(G[pre + "norm2.bias"]), L.ptr(G[pre + "attn.proj.bias"]), M, Dm, st)
             # ---- attention
-            _gemm(gb, wproj_t, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)
+            _gemm(gb, wproj, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(gb, S["att"], G[pre + "attn.proj.weight"], M=Dm, N=Dm, K=M, lda=Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(Dm, Dm, M))
             L.call("passt_attn_bwd", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
                    L.ptr(G[pre + "attn.qkv.bias"]), L.ptr(attn_ws), B, ntok, H, scale, st)   # + qkv bias gradient
-            _gemm(dqkv, wqkv_t, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=3 * Dm, ldc=Dm, mode=0)
+            _gemm(dqkv, wqkv, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(dqkv, S["h1"], G[pre + "attn.qkv.weight"], M=3 * Dm, N=Dm, K=M, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(3 * Dm, Dm, M))
             prev_bias = G[f"blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else None

@@ -446,6 +446,34 @@ def g_attn_bwd_timeline():
         rows=rows)
 
 
+def g_gemm_bkn():
+    """modes 0|16 and 3|16: B operand given as [K, N] row-major."""
+    lib = L.load()
+    torch.manual_seed(6)
+    for (M, N, K) in [(300, 256, 64), (1000, 768, 3072), (30336, 768, 2304), (30336, 3072, 768)]:
+        A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        Bkn = (torch.randn(K, N, device=dev) * 0.5).bfloat16()
+        aux = torch.randn(M, N, device=dev).bfloat16()
+        ref = A.float() @ Bkn.float()
+        rec = dict(test="gemm_bkn", M=M, N=N, K=K)
+        for two in (1, 0):
+            lib.passt_gemm_set_2cta(two)
+            C = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+            gemm(A, Bkn, C, M=M, N=N, K=K, lda=K, ldb=N, ldc=N, mode=16)
+            C3 = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+            cs = torch.zeros(N, device=dev)
+            gemm(A, Bkn, C3, aux=aux, bias=cs, M=M, N=N, K=K, lda=K, ldb=N, ldc=N, mode=3 | 16, ld_aux=N)
+            torch.cuda.synchronize()
+            rec[f"m0_{two}"] = relerr(C, ref)
+            rec[f"m3_{two}"] = relerr(C3, ref * aux.float())
+            rec[f"cs_{two}"] = relerr(cs, (ref * aux.float()).sum(0))
+            if M >= 30000:
+                ms = timeit(lambda: gemm(A, Bkn, C, M=M, N=N, K=K, lda=K, ldb=N, ldc=N, mode=16))
+                rec[f"tflops_{two}"] = 2.0 * M * N * K / ms / 1e9
+        log(**rec)
+    lib.passt_gemm_set_2cta(1)
+
+
 GROUPS = {k[2:]: v for k, v in globals().items() if k.startswith("g_")}
 
 if __name__ == "__main__":
