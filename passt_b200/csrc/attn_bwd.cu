@@ -48,7 +48,8 @@ struct AttnBwdSmem {
   static constexpr int kdST = kQdO + 2 * 32768;      // 32 KB  dS^T (bf16) for the dQ MMA
   static constexpr int kdQ = kdST + 32768;           // 32 KB  fp32 dQ staging; dK/dV staging at item end
   static constexpr int kVec = kdQ + 32768;           // lse/D: 2 x 2 x 128 floats
-  static constexpr int kBars = kVec + 2048;
+  static constexpr int kBias = kVec + 2048;          // per-CTA partial qkv-bias gradient (K and V thirds): 2 x 768 floats
+  static constexpr int kBars = kBias + 2 * 768 * 4;
   static constexpr int kTotal = kBars + 256;
 };
 
@@ -82,6 +83,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sdST = smem + AttnBwdSmem::kdST;
   uint8_t* sdQ = smem + AttnBwdSmem::kdQ;
   float* sVec = reinterpret_cast<float*>(smem + AttnBwdSmem::kVec);
+  float* sBias = reinterpret_cast<float*>(smem + AttnBwdSmem::kBias);   // [0,768): dK sums, [768,1536): dV sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBars);
   uint64_t* kv_full = bars;          // [2]
   uint64_t* kv_empty = bars + 2;     // [2]  tcgen05.commit after the item's last MMA
@@ -111,6 +113,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(kv_ready, 256);
     fence_barrier_init();
   }
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) sBias[i] = 0.f;
   if (warp == 1) tmem_alloc<512>(tmem_holder);
   tc_fence_before();
   __syncthreads();
@@ -351,8 +355,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
           const float sv = warp_colsum32(cv, lane);
           const float sk = warp_colsum32(ck, lane);
-          atomicAdd(p.dbias + 2 * C + h * kBHd + hc * 32 + lane, sv);
-          atomicAdd(p.dbias + C + h * kBHd + hc * 32 + lane, sk);
+          atomicAdd(&sBias[768 + h * kBHd + hc * 32 + lane], sv);    // shared-memory partials, flushed once per CTA
+          atomicAdd(&sBias[h * kBHd + hc * 32 + lane], sk);
         }
       }
       tc_fence_before();
@@ -365,6 +369,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
     if (ct == 0) tma_store_wait<0>();
+    if (p.dbias != nullptr) {
+      named_bar_sync(1, 256);
+      for (int i = ct; i < 2 * 768; i += 256) {
+        const float v = sBias[i];
+        if (v != 0.f) atomicAdd(p.dbias + C + i, v);     // K third at [C, 2C), V third at [2C, 3C)
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -459,6 +470,7 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
                    void* workspace, int B, int N, int H, float scale, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0 || !workspace) return PB_ERR_BAD_ARG;
+  if (dbias_qkv != nullptr && H * kBHd != 768) return PB_ERR_BAD_ARG;   // per-CTA bias partials are sized for C = 768
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int C = H * kBHd;
   float* dq_acc = reinterpret_cast<float*>(workspace);
