@@ -53,13 +53,15 @@ __device__ __forceinline__ void tc_commit_2cta_mc(uint64_t* bar) {
       "h"(uint16_t(3))
       : "memory");
 }
-// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair)
+// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair).  Relaxed: the only thing handed over
+// is tensor memory whose reads have completed (tcgen05.wait::ld + fence::before_thread_sync); a .release here costs a
+// MEMBAR.ALL.GPU per tile per warp that also waits for the epilogue's outstanding bulk stores (profiles/r1_ncu_gemm_epi)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, 0;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
@@ -87,7 +89,8 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufBytes = 32 * 64;
   static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
-  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 2048 + 1024;
+  // after the staging buffers: 256 B pipeline barriers | 256 B per-warp aux barriers | 8 KB column-sum partials | pad
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 256 + 8192 + 1024;
   static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
@@ -108,7 +111,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull_bar = bars + 2 * kStages2;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN] (mode 3 only)
+  uint64_t* aux_bar = bars + 32;              // [kEpiWarps][2] (mode 3: aux block landed in the warp's staging buffer)
+  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2 parity][4 quadrants][BN] (mode 3)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,7 +123,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    if (MODE == kBiasGeluBf16) tma_prefetch_desc(&tmC2);
+    if (MODE == kBiasGeluBf16 || MODE == kGeluGradBf16) tma_prefetch_desc(&tmC2);
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -128,10 +132,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * kEpiWarps);
     }
+    if (MODE == kGeluGradBf16)
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
-  if (MODE == kGeluGradBf16)
-    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_colsum[i] = 0.f;
   if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_holder);
   tc_fence_before();
   cluster_sync_all();
@@ -231,18 +235,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t aphase = 0;
     int buf = 0;
     int tile_parity = 0;
+    uint32_t aux_phase = 0;   // bit b: parity the next wait on this warp's aux barrier b expects
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int split = t / (p.m_tiles * p.n_tiles);
       const int tt = t - split * (p.m_tiles * p.n_tiles);
       const int m_blk = tt / p.n_tiles, n_blk = tt - m_blk * p.n_tiles;
       const int row0 = m_blk * 256 + int(rank) * BM + q * 32;
       const int row = row0 + lane;
+      // mode 3: the gelu' operand (tmC2 is its tensor map) does not depend on the accumulator.  Each warp pulls its
+      // 32x32 blocks with TMA into its own two staging buffers *before* waiting for the tile, reads them back
+      // row-per-lane (same 64 B swizzle as the output), and then reuses the buffer for the output block.
+      if (MODE == kGeluGradBf16) {
+        if (lane == 0) {
+          tma_store_wait_read<0>();          // both staging buffers have been read by the previous tile's stores
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0p = (slot + ci * kEpiSlots) * Cfg::kColsPerChunk;
+            mbar_arrive_expect_tx(&aux_bar[ew * 2 + ci], Cfg::kEpiBufBytes);
+            tma_load_2d(my_epi + ci * Cfg::kEpiBufBytes, &tmC2, &aux_bar[ew * 2 + ci], n_blk * BN + c0p, row0);
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 
 #pragma unroll 1
-      for (int c0 = slot * Cfg::kColsPerChunk; c0 < BN; c0 += kEpiSlots * Cfg::kColsPerChunk) {
+      for (int ci = 0; ci < (BN / Cfg::kColsPerChunk + kEpiSlots - 1) / kEpiSlots; ++ci) {
+        const int c0 = (slot + ci * kEpiSlots) * Cfg::kColsPerChunk;
+        if (c0 >= BN) break;
         const int col0 = n_blk * BN + c0;
         if (!Cfg::kOutF32) {
           uint32_t ra[32];
@@ -256,47 +278,64 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                const float2 lo = add2(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+                const float2 hi = add2(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+                v[i] = lo.x; v[i + 1] = lo.y; v[i + 2] = hi.x; v[i + 3] = hi.y;
               }
             }
           }
           if (MODE == kGeluGradBf16) {
-            if (row < p.M) {
-              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
-                                                               size_t(row) * p.ld_aux + col0);
+            const int ab = ci & 1;               // chunks 0 and 2 use buffer 0, chunk 1 buffer 1
+            if (ci == 1 && slot + 2 * kEpiSlots < BN / Cfg::kColsPerChunk) {
+              // third block of this tile: its aux goes into buffer 0 as soon as block 0's store has read it
+              if (lane == 0) {
+                tma_store_wait_read<0>();
+                const int c0p = (slot + 2 * kEpiSlots) * Cfg::kColsPerChunk;
+                mbar_arrive_expect_tx(&aux_bar[ew * 2], Cfg::kEpiBufBytes);
+                tma_load_2d(my_epi, &tmC2, &aux_bar[ew * 2], n_blk * BN + c0p, row0);
+              }
+              __syncwarp();
+            }
+            mbar_wait(&aux_bar[ew * 2 + ab], (aux_phase >> ab) & 1u);
+            aux_phase ^= (1u << ab);
+            buf = ab;                            // the output block goes back into the buffer the aux came in
+            const uint8_t* abuf = my_epi + ab * Cfg::kEpiBufBytes;
+            // rows >= M arrive as zeros (TMA zero-fills out-of-bounds rows; their accumulator rows are zero as well)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(ap + i);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = *reinterpret_cast<const uint4*>(abuf + lane * 64 + ((uint32_t(i) ^ swz) << 4));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                  v[i * 8 + 2 * j] *= __low2float(h2);
-                  v[i * 8 + 2 * j + 1] *= __high2float(h2);
-                }
+              for (int j = 0; j < 4; ++j) {
+                // bf16 -> fp32 is a 16-bit shift
+                v[i * 8 + 2 * j] *= __uint_as_float(w[j] << 16);
+                v[i * 8 + 2 * j + 1] *= __uint_as_float(w[j] & 0xffff0000u);
               }
             }
             if (p.bias != nullptr) {
-              // bias gradient of the layer that produced `pre`: column sums of this 32x32 block (rows >= M are 0)
+              // bias gradient of the layer that produced `pre`: column sums of this 32x32 block (rows >= M are 0).
+              // One plain store per (quadrant, column): every such slot is written exactly once per tile.
               float cs[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) cs[i] = v[i];
               const float t = warp_colsum32(cs, lane);
-              atomicAdd(&s_colsum[(tile_parity << 8) + c0 + lane], t);
+              s_part[((tile_parity * 4 + q) << 8) + c0 + lane] = t;
             }
           }
           float w2[32];
           if (MODE == kBiasGeluBf16) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float g, dg;
-              gelu_and_grad(v[i], g, dg);
-              v[i] = dg;
-              w2[i] = g;
+            for (int i = 0; i < 32; i += 2) {
+              float2 g, dg;
+              gelu_and_grad2(make_float2(v[i], v[i + 1]), g, dg);
+              v[i] = dg.x; v[i + 1] = dg.y;
+              w2[i] = g.x; w2[i + 1] = g.y;
             }
           }
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
+          if (MODE != kGeluGradBf16) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
           uint8_t* sbuf = my_epi + buf * Cfg::kEpiBufBytes;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
@@ -372,13 +411,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       if (MODE == kGeluGradBf16 && p.bias != nullptr) {
-        // all 12 epilogue warps have added their blocks: flush this tile's 256 column sums, re-zero the buffer
+        // all 12 epilogue warps have stored their partial sums: add the four quadrants and flush this tile's 256
+        // column sums.  The partials are double-buffered by tile parity, so the next tile's stores cannot overtake.
         named_bar_sync(2, kEpiWarps * 32);
         const int et = threadIdx.x - 64;
         if (et < BN) {
-          float* slot = &s_colsum[(tile_parity << 8) + et];
-          atomicAdd(const_cast<float*>(p.bias) + n_blk * BN + et, *slot);
-          *slot = 0.f;
+          const float* pp = &s_part[(tile_parity * 4) << 8];
+          const float t = (pp[et] + pp[256 + et]) + (pp[512 + et] + pp[768 + et]);
+          atomicAdd(const_cast<float*>(p.bias) + n_blk * BN + et, t);
         }
         tile_parity ^= 1;
       }
@@ -435,6 +475,11 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
       return rc;
     if (MODE == kBiasGeluBf16) {
       if ((rc = make_tmap_2d(&tmC2, C2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
+                             CU_TENSOR_MAP_SWIZZLE_64B)))
+        return rc;
+    } else if (MODE == kGeluGradBf16) {
+      if (aux == nullptr || (ld_aux % 8)) return PB_ERR_BAD_ARG;
+      if ((rc = make_tmap_2d(&tmC2, aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ld_aux) * 2, 32, 32,
                              CU_TENSOR_MAP_SWIZZLE_64B)))
         return rc;
     } else {

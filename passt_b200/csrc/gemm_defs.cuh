@@ -61,6 +61,57 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
 }
 
 
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ----
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
+// gelu_and_grad on two values at once.  Same Abramowitz-Stegun 7.1.26 evaluation, rearranged so that everything
+// except the two rcp and two ex2 runs as packed FFMA2/FMUL2 (11 issue slots per element instead of 20):
+//   k = sqrt(log2(e)/2),  y = k|x|  (so exp(-x^2/2) = 2^(-y^2)),  t = 1/(1 + (p/(k sqrt 2)) y),
+//   w = (Phi(|x|) - 1/2)/k = 1/(2k) - (1/(2k)) (a1 t + ... + a5 t^5) 2^(-y^2),   Phi(x) = 1/2 + copysign(k, x) w.
+__device__ __forceinline__ void gelu_and_grad2(float2 x, float2& g, float2& dg) {
+  constexpr float k = 0.84932180028801904f;                       // sqrt(0.5 * log2(e))
+  constexpr float pk = 0.3275911f * 0.70710678118654752f / k;
+  constexpr float hk = 0.5f / k;
+  const float2 ks = make_float2(__uint_as_float((__float_as_uint(x.x) & 0x80000000u) | __float_as_uint(k)),
+                                __uint_as_float((__float_as_uint(x.y) & 0x80000000u) | __float_as_uint(k)));
+  const float2 y = mul2(x, ks);
+  const float2 d = fma2(y, make_float2(pk, pk), make_float2(1.f, 1.f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  const float2 yy = mul2(y, y);
+  const float2 e = make_float2(fast_ex2(-yy.x), fast_ex2(-yy.y));
+  float2 q = fma2(make_float2(-1.061405429f * hk, -1.061405429f * hk), t, make_float2(1.453152027f * hk, 1.453152027f * hk));
+  q = fma2(q, t, make_float2(-1.421413741f * hk, -1.421413741f * hk));
+  q = fma2(q, t, make_float2(0.284496736f * hk, 0.284496736f * hk));
+  q = fma2(q, t, make_float2(-0.254829592f * hk, -0.254829592f * hk));
+  const float2 w = fma2(mul2(q, t), e, make_float2(hk, hk));
+  const float2 cdf = fma2(ks, w, make_float2(0.5f, 0.5f));
+  g = mul2(x, cdf);
+  dg = fma2(mul2(x, e), make_float2(0.3989422804014327f, 0.3989422804014327f), cdf);
+}
+
 // 32 lanes x 32 values -> lane i ends up with the sum over all lanes of value i (butterfly: 31 shuffles)
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll

@@ -18,9 +18,12 @@ namespace pb {
 constexpr int kNfft = 1024;
 constexpr int kHalf = 512;
 constexpr int kMelBins = 128;
-constexpr int kMaxW = 64;  // max non-zeros per triangular filter we support
-constexpr int kFramesPerCta = 32;
-constexpr int kMelWarps = 8;
+constexpr int kMaxW = 32;        // max non-zeros per triangular filter (widest PaSST filter: 28 taps at fmax = 16 kHz)
+constexpr int kMelWarps = 12;
+constexpr int kFramesPerRound = 48;   // 4 frames per warp, staged and stored as 48-frame rows
+constexpr int kRoundsPerCta = 2;
+constexpr int kFramesPerCta = kFramesPerRound * kRoundsPerCta;
+constexpr int kFftPad = kHalf + kHalf / 8;   // padded per-warp FFT buffer: phys(i) = i + (i >> 3)
 
 struct MelTables {
   float2 tw1024[1024];  // exp(-2*pi*i*m/1024)
@@ -138,7 +141,10 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   v[3] = cadd(b6, b7); v[7] = csub(b6, b7);
 }
 
-// one Stockham radix-8 pass over a 512-point buffer held by one warp (in place via registers)
+__device__ __forceinline__ int fphys(int i) { return i + (i >> 3); }   // bank-conflict-free padding of the FFT buffer
+
+// one Stockham radix-8 pass over a 512-point buffer held by one warp (in place via registers).
+// tw: per-pass twiddle table laid out [r-1][k] (k contiguous) so that lanes read consecutive addresses.
 template <int Ns>
 __device__ __forceinline__ void radix8_pass(float2* buf, const float2* tw, int lane) {
   float2 v[2][8];
@@ -146,12 +152,11 @@ __device__ __forceinline__ void radix8_pass(float2* buf, const float2* tw, int l
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[h][r] = buf[j + 64 * r];
+    for (int r = 0; r < 8; ++r) v[h][r] = buf[fphys(j + 64 * r)];
     if (Ns > 1) {
       const int k = j % Ns;
-      // exp(-2*pi*i*r*k/(8*Ns)) = tw1024[r*k*(1024/(8*Ns))]
 #pragma unroll
-      for (int r = 1; r < 8; ++r) v[h][r] = cmul(v[h][r], tw[r * k * (1024 / (8 * Ns))]);
+      for (int r = 1; r < 8; ++r) v[h][r] = cmul(v[h][r], tw[(r - 1) * Ns + k]);   // exp(-2*pi*i*r*k/(8*Ns))
     }
     dft8(v[h]);
   }
@@ -161,7 +166,7 @@ __device__ __forceinline__ void radix8_pass(float2* buf, const float2* tw, int l
     const int j = lane + 32 * h;
     const int base = (j / Ns) * Ns * 8 + (j % Ns);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) buf[base + r * Ns] = v[h][r];
+    for (int r = 0; r < 8; ++r) buf[fphys(base + r * Ns)] = v[h][r];
   }
   __syncwarp();
 }
@@ -175,30 +180,50 @@ struct MelParams {
   float preemph;      // 0.97
 };
 
-__global__ void __launch_bounds__(kMelWarps * 32)
+struct MelSmem {
+  static constexpr int kTw = 0;                                  // 512 float2: exp(-2 pi i k / 1024), untangle
+  static constexpr int kT2 = kTw + 512 * 8;                      // 7 x 8  float2: pass-2 twiddles
+  static constexpr int kT3 = kT2 + 7 * 8 * 8;                    // 7 x 64 float2: pass-3 twiddles
+  static constexpr int kWin = kT3 + 7 * 64 * 8;                  // 1024 floats
+  static constexpr int kWT = kWin + 1024 * 4;                    // kMaxW x 128 floats
+  static constexpr int kLo = kWT + kMaxW * kMelBins * 4;         // 128 ints
+  static constexpr int kCnt = kLo + kMelBins * 4;
+  static constexpr int kOut = kCnt + kMelBins * 4;               // 128 x (kFramesPerRound + 1) floats
+  static constexpr int kFft = kOut + kMelBins * (kFramesPerRound + 1) * 4;
+  static constexpr int kTotal = kFft + kMelWarps * kFftPad * 8;
+};
+
+__global__ void __launch_bounds__(kMelWarps * 32, 2)
 mel_kernel(const MelParams p, const MelTables* __restrict__ tabs, const MelBank* __restrict__ bank) {
-  extern __shared__ uint8_t smem_raw[];
-  float2* s_tw = reinterpret_cast<float2*>(smem_raw);                 // 1024 float2 = 8 KB
-  float* s_win = reinterpret_cast<float*>(s_tw + 1024);               // 1024 floats = 4 KB
-  float* s_wT = s_win + 1024;                                         // kMaxW*128 floats = 32 KB
-  int* s_lo = reinterpret_cast<int*>(s_wT + kMaxW * kMelBins);        // 128
-  int* s_cnt = s_lo + kMelBins;                                       // 128
-  float* s_out = reinterpret_cast<float*>(s_cnt + kMelBins);          // 128 x 33
-  float2* s_fft = reinterpret_cast<float2*>(s_out + kMelBins * 33);   // 8 warps x 512 float2 = 32 KB
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw + MelSmem::kTw);
+  float2* s_t2 = reinterpret_cast<float2*>(smem_raw + MelSmem::kT2);
+  float2* s_t3 = reinterpret_cast<float2*>(smem_raw + MelSmem::kT3);
+  float* s_win = reinterpret_cast<float*>(smem_raw + MelSmem::kWin);
+  float* s_wT = reinterpret_cast<float*>(smem_raw + MelSmem::kWT);
+  int* s_lo = reinterpret_cast<int*>(smem_raw + MelSmem::kLo);
+  int* s_cnt = reinterpret_cast<int*>(smem_raw + MelSmem::kCnt);
+  float* s_out = reinterpret_cast<float*>(smem_raw + MelSmem::kOut);
+  float2* s_fft = reinterpret_cast<float2*>(smem_raw + MelSmem::kFft);
+  constexpr int kOutLd = kFramesPerRound + 1;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kFramesPerCta;
 
-  for (int i = tid; i < 1024; i += blockDim.x) { s_tw[i] = tabs->tw1024[i]; s_win[i] = tabs->win[i]; }
+  for (int i = tid; i < 512; i += blockDim.x) s_tw[i] = tabs->tw1024[i];
+  for (int i = tid; i < 7 * 8; i += blockDim.x) s_t2[i] = tabs->tw1024[(i / 8 + 1) * (i % 8) * 16];
+  for (int i = tid; i < 7 * 64; i += blockDim.x) s_t3[i] = tabs->tw1024[(i / 64 + 1) * (i % 64) * 2];
+  for (int i = tid; i < 1024; i += blockDim.x) s_win[i] = tabs->win[i];
   for (int i = tid; i < kMaxW * kMelBins; i += blockDim.x) s_wT[i] = bank->wT[i];
   if (tid < kMelBins) { s_lo[tid] = bank->lo[tid]; s_cnt[tid] = bank->cnt[tid]; }
+  const bool bank_overflow = bank->overflow != 0;   // a filter wider than kMaxW taps: poison the output, never truncate silently
   __syncthreads();
 
   const float* x = p.wave + size_t(b) * p.L;
   const int Ly = p.L - 1;  // pre-emphasised length
-  float2* buf = s_fft + warp * kHalf;
-  float* pw = reinterpret_cast<float*>(buf);  // power spectrum reuses the FFT buffer
+  float2* buf = s_fft + warp * kFftPad;
+  float* pw = reinterpret_cast<float*>(buf);  // power spectrum reuses the FFT buffer (512 floats, unpadded)
+  const bool vec_ok = ((p.L & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
 
   // per-example SpecAugment bands (torchaudio mask_along_axis_iid: start=floor(min), end=start+floor(value))
   int f_lo = 0, f_hi = 0, m_lo = 0, m_hi = 0;
@@ -215,84 +240,96 @@ mel_kernel(const MelParams p, const MelTables* __restrict__ tabs, const MelBank*
     }
   }
 
-  for (int fi = warp; fi < kFramesPerCta; fi += kMelWarps) {
-    const int t = t0 + fi;
-    if (t >= p.T) break;  // warp-uniform
-    // ---- load: z[n] = f[2n] + i f[2n+1], f[m] = win[m] * y[t*hop - 512 + m], y = pre-emphasised, reflect pad
-    const int j0 = t * p.hop - kNfft / 2;
+  for (int round = 0; round < kRoundsPerCta; ++round) {
+    const int t0 = blockIdx.x * kFramesPerCta + round * kFramesPerRound;
+    if (t0 >= p.T) break;   // block-uniform
+    for (int fi = warp; fi < kFramesPerRound; fi += kMelWarps) {
+      const int t = t0 + fi;
+      if (t >= p.T) break;  // warp-uniform
+      // ---- load: z[n] = f[2n] + i f[2n+1], f[m] = win[m] * y[t*hop - 512 + m], y = pre-emphasised, reflect pad
+      const int j0 = t * p.hop - kNfft / 2;
+      const bool interior = vec_ok && j0 >= 0 && (j0 + kNfft + 2) <= Ly && ((j0 & 1) == 0);
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int n = lane + 32 * i;
-      float2 z;
-      {
-        float v[2];
+      for (int i = 0; i < 16; ++i) {
+        const int n = lane + 32 * i;
+        const float w0 = s_win[2 * n], w1 = s_win[2 * n + 1];
+        float2 z = make_float2(0.f, 0.f);
+        if (w0 != 0.f || w1 != 0.f) {
+          if (interior) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(x + j0 + 2 * n));
+            const float c = __ldg(x + j0 + 2 * n + 2);
+            z.x = w0 * (a.y - p.preemph * a.x);
+            z.y = w1 * (c - p.preemph * a.y);
+          } else {
+            float v[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int m = 2 * n + e;
-          const float w = s_win[m];
-          float val = 0.f;
-          if (w != 0.f) {
-            int j = j0 + m;
-            if (j < 0) j = -j;
-            if (j >= Ly) j = 2 * (Ly - 1) - j;
-            const float x0 = __ldg(x + j), x1 = __ldg(x + j + 1);
-            val = w * (x1 - p.preemph * x0);
+            for (int e = 0; e < 2; ++e) {
+              const float w = e ? w1 : w0;
+              float val = 0.f;
+              if (w != 0.f) {
+                int j = j0 + 2 * n + e;
+                if (j < 0) j = -j;
+                if (j >= Ly) j = 2 * (Ly - 1) - j;
+                const float x0 = __ldg(x + j), x1 = __ldg(x + j + 1);
+                val = w * (x1 - p.preemph * x0);
+              }
+              v[e] = val;
+            }
+            z = make_float2(v[0], v[1]);
           }
-          v[e] = val;
         }
-        z = make_float2(v[0], v[1]);
+        buf[fphys(n)] = z;
       }
-      buf[n] = z;
-    }
-    __syncwarp();
-    // ---- 512-point complex FFT
-    radix8_pass<1>(buf, s_tw, lane);
-    radix8_pass<8>(buf, s_tw, lane);
-    radix8_pass<64>(buf, s_tw, lane);
-    // ---- untangle to the 1024-point real spectrum, power for bins 0..511
-    float pk[16];
+      __syncwarp();
+      // ---- 512-point complex FFT
+      radix8_pass<1>(buf, s_t2, lane);
+      radix8_pass<8>(buf, s_t2, lane);
+      radix8_pass<64>(buf, s_t3, lane);
+      // ---- untangle to the 1024-point real spectrum, power for bins 0..511
+      float pk[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int k = lane + 32 * i;
-      const float2 zk = buf[k];
-      float2 zc = buf[(kHalf - k) & (kHalf - 1)];
-      zc.y = -zc.y;
-      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-      const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
-      const float2 o = make_float2(d.y, -d.x);  // -i * d
-      const float2 xo = cmul(s_tw[k], o);
-      const float re = e.x + xo.x, im = e.y + xo.y;
-      pk[i] = re * re + im * im;
-    }
-    __syncwarp();
+      for (int i = 0; i < 16; ++i) {
+        const int k = lane + 32 * i;
+        const float2 zk = buf[fphys(k)];
+        float2 zc = buf[fphys((kHalf - k) & (kHalf - 1))];
+        zc.y = -zc.y;
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+        const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+        const float2 o = make_float2(d.y, -d.x);  // -i * d
+        const float2 xo = cmul(s_tw[k], o);
+        const float re = e.x + xo.x, im = e.y + xo.y;
+        pk[i] = re * re + im * im;
+      }
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) pw[lane + 32 * i] = pk[i];
-    __syncwarp();
-    // ---- sparse triangular filterbank + log + masks + affine
+      for (int i = 0; i < 16; ++i) pw[lane + 32 * i] = pk[i];
+      __syncwarp();
+      // ---- sparse triangular filterbank + log + masks + affine
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = lane + 32 * i;
-      const int lo = s_lo[m], cnt = s_cnt[m];
-      float acc = 0.f;
-      for (int j = 0; j < cnt; ++j) acc = fmaf(s_wT[j * kMelBins + m], pw[lo + j], acc);
-      float v = logf(acc + 1e-5f);
-      if ((m >= f_lo && m < f_hi) || (t >= m_lo && t < m_hi)) v = 0.f;
-      s_out[m * 33 + fi] = (v + 4.5f) / 5.0f;
+      for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        const int lo = s_lo[m], cnt = s_cnt[m];
+        float acc = 0.f;
+        for (int j = 0; j < cnt; ++j) acc = fmaf(s_wT[j * kMelBins + m], pw[lo + j], acc);
+        float v = logf(acc + 1e-5f);
+        if ((m >= f_lo && m < f_hi) || (t >= m_lo && t < m_hi)) v = 0.f;
+        s_out[m * kOutLd + fi] = bank_overflow ? __int_as_float(0x7fc00000) : (v + 4.5f) / 5.0f;
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  __syncthreads();
-  // ---- coalesced store: 32 consecutive frames per mel row
-  const int nt = min(kFramesPerCta, p.T - t0);
-  float* o = p.out + size_t(b) * kMelBins * p.T + t0;
-  for (int idx = tid; idx < kMelBins * 32; idx += blockDim.x) {
-    const int m = idx >> 5, f = idx & 31;
-    if (f < nt) o[size_t(m) * p.T + f] = s_out[m * 33 + f];
+    __syncthreads();
+    // ---- coalesced store: up to 48 consecutive frames per mel row
+    const int nt = min(kFramesPerRound, p.T - t0);
+    float* o = p.out + size_t(b) * kMelBins * p.T + t0;
+    for (int idx = tid; idx < kMelBins * kFramesPerRound; idx += blockDim.x) {
+      const int m = idx / kFramesPerRound, f = idx - m * kFramesPerRound;
+      if (f < nt) o[size_t(m) * p.T + f] = s_out[m * kOutLd + f];
+    }
+    __syncthreads();
   }
 }
 
-constexpr int kMelSmemBytes = 1024 * 8 + 1024 * 4 + kMaxW * kMelBins * 4 + 2 * kMelBins * 4 + kMelBins * 33 * 4 +
-                              kMelWarps * kHalf * 8;
+constexpr int kMelSmemBytes = MelSmem::kTotal;
 
 }  // namespace pb
 
