@@ -89,8 +89,9 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufBytes = 32 * 64;
   static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
-  // after the staging buffers: 256 B pipeline barriers | 256 B per-warp aux barriers | 8 KB column-sum partials | pad
-  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 256 + 8192 + 1024;
+  // after the staging buffers: 256 B pipeline barriers | 256 B per-warp aux barriers | 8 KB column-sum partials |
+  // 128 B per epilogue warp for the bias values of its current block | pad
+  static constexpr int kSmemBytes = kStages2 * kStageBytes + kEpiBytes + 256 + 256 + 8192 + kEpiWarps * 128 + 1024;
   static constexpr int kColsPerChunk = kOutF32 ? 16 : 32;
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
@@ -113,6 +114,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* aux_bar = bars + 32;              // [kEpiWarps][2] (mode 3: aux block landed in the warp's staging buffer)
   float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2 parity][4 quadrants][BN] (mode 3)
+  float* s_biasw = s_part + 2 * 4 * BN;       // [kEpiWarps][32] (modes 0/1: bias of the block a warp is working on)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -257,6 +259,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
       }
+      // modes 0/1: lane i fetches bias[col0 + i] of the block one step ahead (here: the tile's first block, before the
+      // wait), so that the L2 latency never sits between the accumulator load and its first use
+      float bias_next = 0.f;
+      const bool has_bias = (MODE == kBiasBf16 || MODE == kBiasGeluBf16) && p.bias != nullptr;
+      if (has_bias) bias_next = __ldg(p.bias + n_blk * BN + slot * Cfg::kColsPerChunk + lane);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
@@ -269,15 +276,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (!Cfg::kOutF32) {
           uint32_t ra[32];
           tmem_ld_x32(taddr + c0, ra);
+          if (has_bias) {
+            // broadcast this block's 32 bias values through the warp's smem slot; prefetch the next block's
+            s_biasw[ew * 32 + lane] = bias_next;
+            const int c0n = c0 + kEpiSlots * Cfg::kColsPerChunk;
+            if (c0n < BN) bias_next = __ldg(p.bias + n_blk * BN + c0n + lane);
+            __syncwarp();
+          }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
           if (MODE == kBiasBf16 || MODE == kBiasGeluBf16) {
-            if (p.bias) {
+            if (has_bias) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                const float4 b4 = *reinterpret_cast<const float4*>(s_biasw + ew * 32 + i);
                 const float2 lo = add2(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
                 const float2 hi = add2(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
                 v[i] = lo.x; v[i + 1] = lo.y; v[i + 2] = hi.x; v[i + 3] = hi.y;
