@@ -84,6 +84,13 @@ int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dne
                           int Fg, int Tg, int toff, const int* toff_dev, void* stream);
 /* f32 [R,C] -> bf16 [R,C] and bf16 [C,R] (tensor-core operand copies of the fp32 master weights) */
 int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R, int C, void* stream);
+
+/* fp32 -> bf16 of a list of matrices in ONE launch (the per-step refresh of every bf16 weight copy; replaces the
+ * reference's per-op autocast casts, torch/amp autocast of F.linear at models/passt.py:285-289,345,359).
+ * table: device array of n_entries 32-byte records {const float* src; void* dst_bf16; uint64_t n8; uint32_t
+ * first_block; uint32_t pad}, n8 = elements / 8, first_block = running sum of ceil(n8 / 1024); total_blocks = the
+ * final sum. */
+int passt_cast_multi(const void* table, int n_entries, int total_blocks, void* stream);
 /* final norm on cls/dist rows, (cls+dist)/2, head LayerNorm + Linear (models/passt.py:570-588, :463-464) */
 int passt_head_fwd(const float* x, const void* delta_bf16, const float* norm_g, const float* norm_b,
                    const float* hln_g, const float* hln_b, const float* W, const float* bias, float* logits,

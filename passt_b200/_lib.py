@@ -33,6 +33,7 @@ _SIGS = {
     "passt_token_table": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "passt_cast_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
+    "passt_cast_multi": (i32, [vp, i32, i32, vp]),
     "passt_head_fwd": (i32, [vp] * 11 + [i32, i32, i32, vp]),
     "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),
     "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),

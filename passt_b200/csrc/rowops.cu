@@ -325,6 +325,49 @@ cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, 
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// fp32 -> bf16 for a whole list of matrices in one launch.  table[e] = {src, dst, n8, first_block}; block b works on
+// 1024 8-element groups of the entry whose [first_block, next first_block) range contains it.
+struct CastEntry {
+  const float* src;
+  __nv_bfloat16* dst;
+  unsigned long long n8;
+  unsigned int first_block, pad;
+};
+constexpr int kCastGroupsPerBlock = 1024;   // 256 threads x 4 groups of 8 elements
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const CastEntry* __restrict__ table, int n_entries) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {                       // last entry with first_block <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_e = lo;
+  }
+  __syncthreads();
+  const CastEntry e = table[s_e];
+  const size_t g0 = size_t(blockIdx.x - e.first_block) * kCastGroupsPerBlock;
+  const float4* in = reinterpret_cast<const float4*>(e.src);
+  uint4* out = reinterpret_cast<uint4*>(e.dst);
+  float4 a[4], b[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const size_t i = g0 + u * 256 + threadIdx.x;
+    if (i < e.n8) { a[u] = in[2 * i]; b[u] = in[2 * i + 1]; }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const size_t i = g0 + u * 256 + threadIdx.x;
+    if (i < e.n8) {
+      uint4 o;
+      o.x = pack_bf16(a[u].x, a[u].y); o.y = pack_bf16(a[u].z, a[u].w);
+      o.z = pack_bf16(b[u].x, b[u].y); o.w = pack_bf16(b[u].z, b[u].w);
+      out[i] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // classifier head
 // ------------------------------------------------------------------------------------------------
@@ -393,17 +436,31 @@ head_fwd_kernel(const HeadParams p, float* __restrict__ logits, float* __restric
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int cls = warp; cls < p.C; cls += 8) {
-    const float* w = p.W + size_t(cls) * D;
-    float acc = 0.f;
+  // four classes per pass: 24 independent 16-byte loads in flight per lane (the weight rows come from L2)
+  float fr[D / 128][4];
 #pragma unroll
-    for (int i = 0; i < D / 128; ++i) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + i * 128 + lane * 4));
-      const float* f = s_fl + i * 128 + lane * 4;
-      acc += wv.x * f[0] + wv.y * f[1] + wv.z * f[2] + wv.w * f[3];
+  for (int i = 0; i < D / 128; ++i) {
+    const float4 f4 = *reinterpret_cast<const float4*>(s_fl + i * 128 + lane * 4);
+    fr[i][0] = f4.x; fr[i][1] = f4.y; fr[i][2] = f4.z; fr[i][3] = f4.w;
+  }
+  for (int cls0 = warp * 4; cls0 < p.C; cls0 += 32) {
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[u] = 0.f;
+      const int cls = min(cls0 + u, p.C - 1);
+      const float* w = p.W + size_t(cls) * D;
+#pragma unroll
+      for (int i = 0; i < D / 128; ++i) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + i * 128 + lane * 4));
+        acc[u] += wv.x * fr[i][0] + wv.y * fr[i][1] + wv.z * fr[i][2] + wv.w * fr[i][3];
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) logits[size_t(b) * p.C + cls] = acc + p.bias[cls];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(acc[u]);
+      if (lane == 0 && cls0 + u < p.C) logits[size_t(b) * p.C + cls0 + u] = t + p.bias[cls0 + u];
+    }
   }
 }
 
@@ -448,7 +505,8 @@ head_bwd_kernel(const HeadParams p, const float* __restrict__ dlogits, const flo
   for (int c = tid; c < p.C; c += 256) s_dl[c] = dlogits ? dlogits[size_t(b) * p.C + c] : 0.f;
   __syncthreads();
   float dfl[3] = {0.f, 0.f, 0.f};
-  for (int cls = 0; cls < p.C; ++cls) {
+#pragma unroll 8
+  for (int cls = 0; cls < p.C; ++cls) {   // unrolled: 24 independent L2 loads in flight per thread
     const float dl = s_dl[cls];
     const float* w = p.W + size_t(cls) * D;
 #pragma unroll
@@ -620,6 +678,18 @@ int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R
   }
   cast_transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
       in, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)outT_bf16, R, C);
+  PB_LAUNCH_CHECK();
+  return 0;
+}
+
+// table: device array of n_entries records {const float* src; bf16* dst; uint64 n8; uint32 first_block; uint32 pad}
+// (32 bytes each; n8 = elements / 8; first_block = running sum of ceil(n8 / 1024)); total_blocks = that sum's end.
+int passt_cast_multi(const void* table, int n_entries, int total_blocks, void* stream) {
+  using namespace pb;
+  static_assert(sizeof(CastEntry) == 32, "CastEntry layout is part of the C ABI");
+  if (table == nullptr || n_entries <= 0 || total_blocks <= 0) return PB_ERR_BAD_ARG;
+  cast_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const CastEntry*>(table),
+                                                                    n_entries);
   PB_LAUNCH_CHECK();
   return 0;
 }

@@ -93,7 +93,7 @@ class WeightCache:
 
     Staleness cannot be detected from ``Tensor._version``: fused CUDA optimizers (torch.optim.AdamW(fused=True))
     and CUDA-graph replays update parameters without bumping it.  Policy: every *training* forward refreshes
-    unconditionally (``force=True``; 49 small kernels, ~0.1 ms) and marks the cache dirty; the next no-grad forward
+    unconditionally (one multi-matrix cast launch, ``refresh_all``) and marks the cache dirty; the next no-grad forward
     refreshes once more (the optimizer ran after the last training forward) and clears the flag.  In-place edits
     that do bump the version (load_state_dict, SWA averaging, manual ``p.data`` changes via ops) are caught by the
     version check as well."""
@@ -119,9 +119,45 @@ class WeightCache:
         self._store[key] = (ver, wb, wt)
         return wb, wt
 
+    def refresh_all(self, params):
+        """Re-cast every matrix in ``params`` with ONE launch (passt_cast_multi).  The pointer table lives on the device
+        and is rebuilt only when a parameter or its bf16 copy moved; building it is host work (one small H2D copy),
+        so it must first happen outside CUDA-graph capture -- the eager warm-up steps do that."""
+        recs, ents = [], []
+        for p in params:
+            key = (p.data_ptr(), tuple(p.shape))
+            ent = self._store.get(key)
+            n = p.numel()
+            if n % 8 != 0 or (ent is not None and ent[2] is not None):
+                self.get(p, False, True)         # odd size or a transposed copy to keep fresh: per-matrix path
+                continue
+            if ent is None or ent[1].device != p.device:
+                wb = torch.empty(p.shape[0], n // p.shape[0], dtype=BF16, device=p.device)
+            else:
+                wb = ent[1]
+            recs.append((p.data_ptr(), wb.data_ptr(), n // 8))
+            ents.append((key, p, wb))
+        if not recs:
+            return
+        sig = tuple(recs)
+        if getattr(self, "_table_sig", None) != sig:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("passt_b200: the bf16 weight table changed during CUDA-graph capture; run one eager "
+                                   "training step before capturing")
+            rows, blk = [], 0
+            for src, dst, n8 in recs:
+                rows.append([src, dst, n8, blk])      # first_block in the low 32 bits of the 4th word, pad = 0
+                blk += (n8 + 1023) // 1024
+            self._table = torch.tensor(rows, dtype=torch.int64).to(ents[0][1].device)
+            self._table_sig, self._table_blocks = sig, blk
+        L.call("passt_cast_multi", L.ptr(self._table), len(recs), self._table_blocks, L.stream_ptr())
+        for key, p, wb in ents:
+            self._store[key] = ((p.data_ptr(), p._version), wb, None)
+
     def clear(self):
         self._store.clear()
         self.dirty = False
+        self._table_sig = None
 
     def invalidate(self):
         """Force a refresh on next use (parameters were updated without Python seeing it, e.g. by a graph replay)."""
@@ -223,7 +259,11 @@ class PasstFunction(torch.autograd.Function):
                L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
                L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset,
                L.ptr(plan.toffset_dev), st)
-        wpe, _ = wc.get(P["patch_embed.proj.weight"], False, refresh)
+        if refresh:
+            wnames = ["patch_embed.proj.weight"] + [f"blocks.{i}.{w}.weight" for i in range(depth)
+                                                    for w in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]
+            wc.refresh_all([P[n] for n in wnames])
+        wpe, _ = wc.get(P["patch_embed.proj.weight"], False)
         xcur = torch.empty(M, Dm, **f32)
         _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
 
@@ -232,10 +272,10 @@ class PasstFunction(torch.autograd.Function):
         scale = float((Dm // H) ** -0.5)
         for i in range(depth):
             pre = f"blocks.{i}."
-            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], False, refresh)
-            wproj, _ = wc.get(P[pre + "attn.proj.weight"], False, refresh)
-            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], False, refresh)
-            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], False, refresh)
+            wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], False)
+            wproj, _ = wc.get(P[pre + "attn.proj.weight"], False)
+            wfc1, _ = wc.get(P[pre + "mlp.fc1.weight"], False)
+            wfc2, _ = wc.get(P[pre + "mlp.fc2.weight"], False)
             # x_in = xcur (+ delta of the previous block); h1 = LN1(x_in)
             h1 = torch.empty(M, Dm, **b16)
             mean1 = torch.empty(M, **f32); rstd1 = torch.empty(M, **f32)
