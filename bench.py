@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ======================================================================================================
@@ -410,11 +410,32 @@ def run_candidate(args, rank, local_rank, world):
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "clips/s", "cores": CPU_THREADS, "kind": "port",
                                     "sample": "3 x 1-clip train step after 1 warm-up (mel + fwd + bwd + AdamW) of the CPU oracle port, fp32"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     return line
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """Everything except the one JSON line goes to stderr -- including what C libraries write to fd 1 (NCCL prints
+    its version banner there, the reference frontend prints its FMAX notice)."""
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.write(_REAL_STDOUT_FD, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
