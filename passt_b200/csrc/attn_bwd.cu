@@ -99,6 +99,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_q = (p.N + kTile - 1) / kTile;
   const int C = p.H * kBHd;
+  // the last query tile is trimmed to whole 32-query chunks: S^T / dP^T run with N = qcols_last, the math skips the
+  // unused score columns and dV / dK contract over qcols_last queries (N = 474: 96 instead of 128)
+  const int qcols_last = ((p.N - (n_q - 1) * kTile + 31) / 32) * 32;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQKV); tma_prefetch_desc(&tmdQacc);
@@ -164,6 +167,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       bKmn[s] = make_smem_desc_sw128(smem_u32(sKV + s * 32768), 8192, 1024);   // K as MN-major B (dQ = dS K)
     }
     const uint64_t bdST = make_smem_desc_sw128(smem_u32(sdST), 16384, 1024);   // dS^T as MN-major A (dQ = dS K)
+    const uint32_t id_s_last = make_idesc_bf16(128, qcols_last, 0, 0);
     uint32_t g = 0, n = 0;
     for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
       const uint32_t kb = n & 1;
@@ -174,12 +178,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(&qdo_full[s], (g >> 1) & 1);
         tc_fence_after();
         if (lane == 0) PB_STAMP(1, g * 4 + 0);
+        const bool last_q = (i == n_q - 1);
+        const uint32_t ids = last_q ? id_s_last : id_s;
+        const int n_qk = last_q ? qcols_last / 16 : 8;      // 16-query contraction steps of dV / dK
         if (elect_one()) {
           const uint64_t qk = s ? bQk[1] : bQk[0], dok = s ? bdOk[1] : bdOk[0];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tK + k * 8, qk + uint64_t(k * 2), id_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tK + k * 8, qk + uint64_t(k * 2), ids, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tdP, tV + k * 8, dok + uint64_t(k * 2), id_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tdP, tV + k * 8, dok + uint64_t(k * 2), ids, k > 0);
           tc_commit(sdp_full);
         }
         __syncwarp();
@@ -196,10 +203,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           tc_commit(dq_full);           // dQ first: the compute warps drain it while dV / dK accumulate
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // contraction = queries; 16 queries = 8 TMEM columns of packed bf16
-            umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, domn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
+            if (k < n_qk)
+              umma_bf16_ts(tdV, tS + (k >> 2) * 64 + (k & 3) * 8, domn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, qmn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
+            if (k < n_qk)
+              umma_bf16_ts(tdK, tdP + (k >> 2) * 64 + (k & 3) * 8, qmn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
           tc_commit(&qdo_empty[s]);
           if (i == n_q - 1) {
             tc_commit(dkv_full);
@@ -249,9 +258,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(sdp_full, g & 1);
         tc_fence_after();
         if (ct == 0) PB_STAMP(0, g * 6 + 1);
+        const int q_cols = (i == n_q - 1) ? qcols_last : kTile;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col0 = hc * 64 + c * 32;
+          if (col0 >= q_cols) break;           // trimmed last query tile (warp-uniform)
           uint32_t sv[32], dv[32];
           tmem_ld_x32(tS + lane_addr + col0, sv);
           tmem_ld_x32(tdP + lane_addr + col0, dv);

@@ -68,6 +68,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.N + kKvTile - 1) / kKvTile;
+  // the last key tile is trimmed to whole 32-column chunks: its S MMA runs with N = cols_last, the softmax touches
+  // cols_last / 32 chunks and P V contracts over cols_last keys (N = 474: 96 instead of 128 -> 6 % less exp2 / MMA work)
+  const int cols_last = ((p.N - (n_kv - 1) * kKvTile + 31) / 32) * 32;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -131,14 +134,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int k = 0; k < 8; ++k) dV[s][k] = make_smem_desc_sw128(aV + k * 2048, 8192, 1024);
     }
-    auto issue_s = [&](uint32_t t, uint32_t qs) {
+    const uint32_t idesc_s_last = make_idesc_bf16(128, uint32_t(cols_last), 0, 0);
+    auto issue_s = [&](uint32_t t, uint32_t qs, bool last_tile) {
       const uint32_t s = t & 1;
+      const uint32_t idesc = last_tile ? idesc_s_last : idesc_s;
       mbar_wait(&kv_full[s], (t >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_S, qs ? dQ[1][k] : dQ[0][k], s ? dK[1][k] : dK[0][k], idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_S, qs ? dQ[1][k] : dQ[0][k], s ? dK[1][k] : dK[0][k], idesc, k > 0 ? 1u : 0u);
         tc_commit(s_full);
       }
       __syncwarp();
@@ -148,7 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t qs = n & 1;
       const bool has_next = (it + int(gridDim.x) < p.total_items);
       mbar_wait(&q_full[qs], (n >> 1) & 1);
-      if (n == 0) issue_s(t, qs);              // later items: S of their first tile was issued ahead (below)
+      if (n == 0) issue_s(t, qs, n_kv == 1);   // later items: S of their first tile was issued ahead (below)
       for (int j = 0; j < n_kv; ++j, ++t) {
         const uint32_t s = t & 1;
         mbar_wait(p_full, t & 1);   // P_t is in TMEM and S_t has been consumed
@@ -156,16 +161,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (lane == 0) PB_STAMP(1, t * 3 + 0);
         // next scores first (the softmax warps can start on them while PV_t runs)
         if (j + 1 < n_kv) {
-          issue_s(t + 1, qs);
+          issue_s(t + 1, qs, j + 2 == n_kv);
         } else if (has_next) {
           mbar_wait(&q_full[qs ^ 1], ((n + 1) >> 1) & 1);
-          issue_s(t + 1, qs ^ 1);
+          issue_s(t + 1, qs ^ 1, n_kv == 1);
         }
         if (lane == 0) PB_STAMP(1, t * 3 + 1);
+        const int n_pv = (j + 1 == n_kv) ? cols_last / 16 : 8;   // 16 keys per MMA
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tmem_O, tmem_P + k * 8, s ? dV[1][k] : dV[0][k], idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            if (k < n_pv)
+              umma_bf16_ts(tmem_O, tmem_P + k * 8, s ? dV[1][k] : dV[0][k], idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           tc_commit(o_full);
           tc_commit(&kv_empty[s]);
         }
@@ -189,6 +196,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int j = 0; j < n_kv; ++j, ++t) {
         const int kv_valid = min(kKvTile, p.N - j * kKvTile);
         const bool full_tile = (kv_valid == kKvTile);     // warp-uniform: only the last key tile needs masking
+        const int n_chunks = (j + 1 == n_kv) ? cols_last / 32 : 4;
         mbar_wait(s_full, t & 1);
         tc_fence_after();
         if (warp == 2 && lane == 0) PB_STAMP(0, t * 5 + 0);
@@ -228,6 +236,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+            if (c >= n_chunks) break;            // trimmed last tile (warp-uniform)
             uint32_t v[32];
             tmem_ld_x32(tmem_S + lane_addr + c * 32, v);
             tmem_ld_wait();
