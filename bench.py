@@ -374,6 +374,11 @@ def run_candidate(args, rank, local_rank, world):
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_sustained"]
 
+    # ---- (4) the two other kernels the contract names, timed alone with CUDA events
+    other = None
+    if rank == 0 and world == 1:
+        other = _other_kernel_rooflines(mel, net, dev_waves[0], B, ntok, peaks)
+
     total_clips = B * world * args.steps
     value = total_clips / (ms_dev * 1e-3)
     e2e_value = total_clips / (ms_e2e * 1e-3)
@@ -407,11 +412,62 @@ def run_candidate(args, rank, local_rank, world):
                          "share_of_step": gemm_ms / ms_instr if ms_instr else None,
                          "how": "CUDA events around each GEMM launch in an eager (non-graph) repeat of the timed steps"},
         }
+        if other is not None:
+            line["other_kernels"] = other
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": "clips/s", "cores": CPU_THREADS, "kind": "port",
                                     "sample": "3 x 1-clip train step after 1 warm-up (mel + fwd + bwd + AdamW) of the CPU oracle port, fp32"}
         _emit(line)
     return line
+
+
+def _other_kernel_rooflines(mel, net, wave, B, ntok, peaks):
+    """mel_kernel against the HBM roofline (algorithmic 1.792 MB per clip) and the attention kernels against the
+    tensor roofline (4 / 10 N^2 d flops per clip and head), each timed alone: 3 warm-up + 20 launches."""
+    from passt_b200 import _lib as L
+
+    def avg_ms(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+    was_training = mel.training
+    mel.eval()                       # fixed band, no SpecAugment draws: the launch is the mel kernel alone
+    with torch.no_grad():
+        ms = avg_ms(lambda: mel(wave))
+    mel.train(was_training)
+    gbs = B * 1.792e6 / (ms * 1e-3) / 1e9
+    out["mel_kernel"] = {"bound": "hbm", "ms": ms, "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"],
+                         "note": "fp32 FFT on CUDA cores: issue-bound (~4000 instructions per frame), DESIGN.md 5.3"}
+    H, hd = net.num_heads, net.embed_dim // net.num_heads
+    C = H * hd
+    dev = wave.device
+    qkv = torch.randn(B, ntok, 3 * C, device=dev).bfloat16()
+    o = torch.empty(B, ntok, C, device=dev, dtype=torch.bfloat16)
+    npad = ((ntok + 127) // 128) * 128
+    lse = torch.empty(B, H, npad, device=dev)
+    dO = torch.randn(B, ntok, C, device=dev).bfloat16()
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(L.load().passt_attn_bwd_workspace_bytes(B, ntok, H), dtype=torch.uint8, device=dev)
+    scale = hd ** -0.5
+    ms_f = avg_ms(lambda: L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(o), L.ptr(lse), B, ntok, H, scale, L.stream_ptr()))
+    ms_b = avg_ms(lambda: L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(o), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), None,
+                                 L.ptr(ws), B, ntok, H, scale, L.stream_ptr()))
+    peak = peaks["bf16_sustained"]
+    for name, ms, k in (("attn_fwd_kernel", ms_f, 4.0), ("attn_bwd (D pre-pass + kernel + dQ pack)", ms_b, 10.0)):
+        tf = k * B * H * ntok * ntok * hd / (ms * 1e-3) / 1e12
+        out[name] = {"bound": "tensor", "ms": ms, "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                     "note": "hd=64: one exp2 per score caps the tensor pipe at 50 % (16 ex2/clk/SM), DESIGN.md 5.2"}
+    return out
 
 
 _REAL_STDOUT_FD = None
