@@ -504,14 +504,25 @@ head_bwd_kernel(const HeadParams p, const float* __restrict__ dlogits, const flo
   // ---- d fl = dlogits . W
   for (int c = tid; c < p.C; c += 256) s_dl[c] = dlogits ? dlogits[size_t(b) * p.C + c] : 0.f;
   __syncthreads();
-  float dfl[3] = {0.f, 0.f, 0.f};
+  // threads 0..191 own four consecutive columns each (one 16-byte load per class, eight classes in flight); the
+  // result goes through shared memory back to the strided column ownership of the rest of the kernel
+  __shared__ float s_dfl[D];
+  if (tid < D / 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* w4 = reinterpret_cast<const float4*>(p.W) + tid;
 #pragma unroll 8
-  for (int cls = 0; cls < p.C; ++cls) {   // unrolled: 24 independent L2 loads in flight per thread
-    const float dl = s_dl[cls];
-    const float* w = p.W + size_t(cls) * D;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dfl[i] += dl * __ldg(w + tid + 256 * i);
+    for (int cls = 0; cls < p.C; ++cls) {
+      const float dl = s_dl[cls];
+      const float4 w = __ldg(w4 + size_t(cls) * (D / 4));
+      acc.x = fmaf(dl, w.x, acc.x); acc.y = fmaf(dl, w.y, acc.y);
+      acc.z = fmaf(dl, w.z, acc.z); acc.w = fmaf(dl, w.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(s_dfl + 4 * tid) = acc;
   }
+  __syncthreads();
+  float dfl[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dfl[i] = s_dfl[tid + 256 * i];
   // ---- head LayerNorm backward
   float fh[3], dg[3];
   float sa = 0.f, sb = 0.f;

@@ -5,7 +5,7 @@ determinism for a fixed seed)."""
 import pytest
 import torch
 
-from util import build_net, quiet, relerr
+from util import build_net, depth2_params, quiet, relerr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -126,3 +126,44 @@ def test_bf16_weight_cache_tracks_fused_optimizer_updates():
         a, _ = net(x)
         b, _ = fresh(x)
     assert torch.equal(a, b)
+
+
+def test_stride16_arch_eval_parity():
+    """passt_s_p16_s16_128_ap468 as fine-tuned on FSD50K (fsd50k/README.md:47-77): no patch overlap, grid 8 x 62,
+    200 classes; depth cut to 2 so the CPU oracle stays quick."""
+    O = _oracle()
+    cfg = O.NetCfg(fstride=16, tstride=16, n_classes=200)
+    params = O.synth_params(cfg, seed=11)
+    net = build_net(cfg, params, DEV, arch="passt_s_p16_s16_128_ap468", cut_depth=10).eval()
+    cfg2 = O.NetCfg(fstride=16, tstride=16, n_classes=200, depth=2)
+    torch.manual_seed(2)
+    x = torch.randn(2, 1, 128, 1000)
+    with torch.no_grad():
+        logits, feats = net(x.to(DEV))
+        ref_logits, ref_feats = O.passt_forward(depth2_params(params), x, cfg2, O.StepDraws())
+    assert logits.shape == (2, 200) and net.last_plan.ntok == 8 * 62 + 2
+    assert relerr(logits, ref_logits) < 1e-2 and relerr(feats, ref_feats) < 1e-2
+
+
+def test_waveform_to_logits_wrapper_matches_oracle_chain():
+    """get_basic_model(mode="logits") on raw audio (README.md:49-64 usage: wave[B, samples] @ 32 kHz -> logits):
+    frontend kernel + network against the oracle's mel_frontend + passt_forward, eval mode."""
+    O = _oracle()
+    from passt_b200.wrapper import get_basic_model
+    cfg = O.NetCfg()
+    params = O.synth_params(cfg, seed=13)
+    with quiet():
+        model = get_basic_model(mode="logits", pretrained=False)
+    model.net.load_state_dict(params, strict=True)
+    from passt_b200 import passt as P
+    model.net = P.lighten_model(model.net, cut_depth=10)
+    model = model.to(DEV).eval()
+    torch.manual_seed(4)
+    wave = torch.randn(2, 320000) * 0.1
+    with torch.no_grad():
+        logits = model(wave.to(DEV))
+        mcfg = O.MelCfg()
+        spec = O.mel_frontend(wave, mcfg, O.StepDraws(fmin=0.0, fmax=mcfg.resolved_fmax()), training=False)
+        ref_logits, _ = O.passt_forward(depth2_params(params), spec.unsqueeze(1), O.NetCfg(depth=2), O.StepDraws())
+    assert logits.shape == (2, 527)
+    assert relerr(logits, ref_logits) < 1e-2

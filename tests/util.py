@@ -41,3 +41,19 @@ def build_net(cfg, params, device, arch="passt_s_swa_p16_128_ap476", cut_depth=0
 def oracle_cfg_for_depth(depth, **kw):
     from oracle import passt_oracle as O
     return O.NetCfg(depth=depth, **kw)
+
+
+def depth2_params(params12, last=11):
+    """Oracle-format parameters of the 2-block network lighten_model(cut_depth=10) leaves: block 0 and block `last`
+    (models/passt.py:932-954), renumbered 0, 1."""
+    out = {}
+    for k, v in params12.items():
+        if k.startswith("blocks."):
+            i = int(k.split(".")[1])
+            if i == 0:
+                out[k] = v
+            elif i == last:
+                out[k.replace(f"blocks.{last}.", "blocks.1.")] = v
+        else:
+            out[k] = v
+    return out
