@@ -225,8 +225,12 @@ def run_candidate(args, rank, local_rank, world):
     torch.manual_seed(0)   # identical initial weights on every rank
     net = get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=N_CLASSES, **NET_KW).to(dev).train()
     use_graph = bool(args.graph)
-    opt = torch.optim.AdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=2e-5,
-                            weight_decay=1e-4, fused=True, capturable=use_graph)
+    opt_params = [p for n, p in net.named_parameters() if not n.startswith("head_dist")]
+    if args.optim == "own":
+        from passt_b200.optim import FusedAdamW
+        opt = FusedAdamW(opt_params, lr=2e-5, weight_decay=1e-4).attach(net)
+    else:
+        opt = torch.optim.AdamW(opt_params, lr=2e-5, weight_decay=1e-4, fused=True, capturable=use_graph)
     reducer = GradAllReducer(net) if world > 1 else None
     torch.manual_seed(1000 + rank)
     n_batches = 4
@@ -392,7 +396,9 @@ def run_candidate(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tokens": ntok, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "optimizer": "AdamW(fused) fp32 master weights", "loss": "BCE-with-logits, 527 classes",
+                       "optimizer": ("passt_b200.FusedAdamW (one launch, refreshes the bf16 weight copies), fp32 master weights"
+                                     if args.optim == "own" else "torch.optim.AdamW(fused), fp32 master weights"),
+                       "loss": "BCE-with-logits, 527 classes",
                        "cuda_graph": bool(use_graph),
                        "l2": "4 rotating input batches; per-step working set (~10 GB of activations) >> 126 MB L2",
                        "model_flops_per_step": step_flops,
@@ -497,6 +503,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="candidate", choices=["candidate", "reference"])
+    ap.add_argument("--optim", default="own", choices=["own", "torch"],
+                    help="own: passt_b200.optim.FusedAdamW (default); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the train step as one CUDA graph (default); 0: eager")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

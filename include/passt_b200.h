@@ -91,6 +91,14 @@ int passt_cast_transpose(const float* in, void* out_bf16, void* outT_bf16, int R
  * first_block; uint32_t pad}, n8 = elements / 8, first_block = running sum of ceil(n8 / 1024); total_blocks = the
  * final sum. */
 int passt_cast_multi(const void* table, int n_entries, int total_blocks, void* stream);
+
+/* AdamW over a list of parameter tensors in ONE launch, refreshing the bf16 GEMM-operand copy of a weight in the same
+ * pass (replaces torch.optim.AdamW as built by get_optimizer, ex_audioset.py:104-109, on the training hot path).
+ * table: device array of n_entries 64-byte records {float* p; const float* g; float* m; float* v; void* w16_or_null;
+ * uint64_t n; uint32_t first_block; uint32_t vec; uint64_t reserved}, first_block = running sum of ceil(n / 4096),
+ * vec = 1 when n % 4 == 0 and all pointers are 16-byte aligned; total_blocks = the final sum.
+ * hyper: device float[8] = {lr, beta1, beta2, eps, weight_decay, step, scratch, scratch}; step is advanced here. */
+int passt_adamw_step(const void* table, int n_entries, int total_blocks, float* hyper, void* stream);
 /* final norm on cls/dist rows, (cls+dist)/2, head LayerNorm + Linear (models/passt.py:570-588, :463-464) */
 int passt_head_fwd(const float* x, const void* delta_bf16, const float* norm_g, const float* norm_b,
                    const float* hln_g, const float* hln_b, const float* W, const float* bias, float* logits,

@@ -34,6 +34,7 @@ _SIGS = {
     "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "passt_cast_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
     "passt_cast_multi": (i32, [vp, i32, i32, vp]),
+    "passt_adamw_step": (i32, [vp, i32, i32, vp, vp]),
     "passt_head_fwd": (i32, [vp] * 11 + [i32, i32, i32, vp]),
     "passt_head_bwd": (i32, [vp] * 19 + [i32, i32, i32, vp]),
     "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
@@ -100,7 +101,7 @@ def check(rc: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
+_LAUNCHES = {"passt_adamw_step": 2, "passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
              "passt_attn_bwd_workspace_bytes": 0}
 _launch_counter = 0
 

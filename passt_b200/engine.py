@@ -101,6 +101,9 @@ class WeightCache:
     def __init__(self):
         self._store: Dict[tuple, tuple] = {}
         self.dirty = False
+        # set by passt_b200.optim.FusedAdamW after a step that rewrote the bf16 copies itself: the next forward skips
+        # its own refresh once
+        self.fresh_from_optimizer = False
 
     def get(self, p: torch.Tensor, need_t: bool, force: bool = False):
         key = (p.data_ptr(), tuple(p.shape))
@@ -259,6 +262,9 @@ class PasstFunction(torch.autograd.Function):
                L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
                L.ptr(P["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset,
                L.ptr(plan.toffset_dev), st)
+        if refresh and wc.fresh_from_optimizer:
+            wc.fresh_from_optimizer = False      # FusedAdamW rewrote the copies in its own pass
+            refresh = False
         if refresh:
             wnames = ["patch_embed.proj.weight"] + [f"blocks.{i}.{w}.weight" for i in range(depth)
                                                     for w in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]

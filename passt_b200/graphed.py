@@ -11,7 +11,8 @@ Everything that changes from step to step is data, not launch arguments:
     step = GraphedTrainStep(mel, net, optimizer, loss_fn, example_wave, example_target)
     loss = step(wave, target)            # wave/target: device or pinned-host tensors of the example's shape
 
-The optimizer must be created with ``capturable=True``.  Parity with the eager step: tests/test_gpu_graphed.py.
+The optimizer must be graph-safe: ``passt_b200.optim.FusedAdamW`` or a torch optimizer created with
+``capturable=True``.  Parity with the eager step: tests/test_gpu_graphed.py.
 """
 from __future__ import annotations
 
@@ -94,6 +95,8 @@ class GraphedTrainStep:
         if target is not None:
             self.target.copy_(target, non_blocking=True)
         self._host_draws()
+        if hasattr(self.opt, "sync_hyperparams"):
+            self.opt.sync_hyperparams()       # passt_b200.FusedAdamW: the replayed step reads lr etc. from a pinned mirror
         self.graph.replay()
         self.net._wcache.dirty = True     # the replay updated the parameters: the next eager forward must re-cast
         return self.loss
