@@ -137,3 +137,12 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"{sym} declared in include/passt_b200.h but not exported"
     for sym in _lib.exported_symbols():
         assert sym in declared, f"{sym} bound in _lib.py but not declared in the header"
+
+
+def test_fused_adamw_refuses_cpu_parameters():
+    """No CPU fallback anywhere on the product path: the optimizer says so instead of silently running elsewhere."""
+    import pytest
+    import torch
+    from passt_b200.optim import FusedAdamW
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedAdamW([torch.nn.Parameter(torch.zeros(8))], lr=1e-3)
