@@ -18,8 +18,9 @@ def main():
     torch.manual_seed(0)
     mel = AugmentMelSTFT(freqm=48, timem=192, fmin_aug_range=10, fmax_aug_range=2000).to(dev).train()
     net = get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, s_patchout_t=40, s_patchout_f=4).to(dev).train()
-    opt = torch.optim.AdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=2e-5,
-                            weight_decay=1e-4, fused=True)
+    from passt_b200.optim import FusedAdamW
+    opt = FusedAdamW([p for n, p in net.named_parameters() if not n.startswith("head_dist")], lr=2e-5,
+                     weight_decay=1e-4).attach(net)          # same optimizer as bench.py
     wave = 0.1 * torch.randn(B, 320000, device=dev)
     y = (torch.rand(B, 527, device=dev) < 0.005).float()
 
