@@ -365,6 +365,32 @@ def run_candidate(args, rank, local_rank, world):
         return ms
 
     ms_e2e = timed_once(lambda: e2e_run(args.steps))
+    if os.environ.get("PASST_BENCH_E2E_DIAG") and rank == 0:
+        # where the end-to-end overhead comes from (stderr only): same loop without the H2D copies / the loss read-back
+        def variant(h2d, d2h):
+            def run():
+                cur = torch.cuda.current_stream()
+                for k in range(2):
+                    buf_free[k].record(cur)
+                if h2d:
+                    upload(0)
+                for i in range(args.steps):
+                    k = i & 1
+                    if h2d:
+                        if i + 1 < args.steps:
+                            upload(i + 1)
+                        cur.wait_event(h2d_done[k])
+                    loss = train_step(dev_bufs[k])
+                    buf_free[k].record(cur)
+                    if d2h:
+                        loss_hosts[k].copy_(loss.detach().reshape(1), non_blocking=True)
+                        loss_done[k].record(cur)
+                        if i > 0:
+                            loss_done[k ^ 1].synchronize()
+                torch.cuda.synchronize()
+            return timed_once(run) / args.steps
+        for h2d, d2h in ((True, True), (False, True), (True, False), (False, False)):
+            print(f"[e2e diag] h2d={h2d} d2h={d2h}: {variant(h2d, d2h):.3f} ms/step", file=sys.stderr)
 
     # ---- (3) roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every GEMM launch in a
     #          repeat of the timed steps (kept out of the headline timing so the events do not perturb it)
