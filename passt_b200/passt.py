@@ -234,6 +234,11 @@ class PaSST(nn.Module):
         with torch.cuda.device(x.device):
             plan = self._preset_plan if self._preset_plan is not None else engine.draw_step_plan(self, x, self.training)
             self.last_plan = plan
+            if x.shape[0] == 0:
+                # empty batch: the reference's ops return empty tensors (the random draws above were still consumed)
+                self._mix = None
+                n_cls = self.head[1].out_features
+                return x.new_zeros(0, n_cls, dtype=torch.float32), x.new_zeros(0, self.embed_dim, dtype=torch.float32)
             mix, self._mix = self._mix, None
             logits, feats = engine.PasstFunction.apply(x, self, plan, mix, *self._ordered_params())
         return logits, feats

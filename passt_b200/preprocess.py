@@ -101,6 +101,10 @@ class AugmentMelSTFT(nn.Module):
                 zero = zero if zero is not None else torch.zeros(B, device=x.device)
                 parts += [zero, zero]
             rnd = torch.stack(parts).contiguous()
+        if B == 0:
+            # empty batch: same draws as above, empty result (torch.stft-based reference: [0, n_mels, T])
+            self.last_draws = (fmin, fmax, rnd)
+            return torch.empty(0, self.n_mels, 1 + (Lw - 1) // self.hopsize, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             ent = self._workspace(x.device)
             st = L.stream_ptr()

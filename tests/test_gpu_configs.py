@@ -167,3 +167,22 @@ def test_waveform_to_logits_wrapper_matches_oracle_chain():
         ref_logits, _ = O.passt_forward(depth2_params(params), spec.unsqueeze(1), O.NetCfg(depth=2), O.StepDraws())
     assert logits.shape == (2, 527)
     assert relerr(logits, ref_logits) < 1e-2
+
+
+def test_empty_batch_returns_empty_outputs():
+    """B = 0 goes through like in the reference (empty tensors), consuming the same random draws."""
+    from passt_b200.passt import get_model
+    from passt_b200.preprocess import AugmentMelSTFT
+    with quiet():
+        net = get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, s_patchout_t=40, s_patchout_f=4).to(DEV).train()
+        mel = AugmentMelSTFT(fmin_aug_range=10, fmax_aug_range=2000).to(DEV).train()
+    torch.manual_seed(3)
+    spec = mel(torch.zeros(0, 320000, device=DEV))
+    assert spec.shape == (0, 128, 1000)
+    logits, feats = net(spec.unsqueeze(1))
+    assert logits.shape == (0, 527) and feats.shape == (0, 768)
+    after_empty = torch.randint(1 << 30, (1,)).item()
+    torch.manual_seed(3)
+    spec = mel(torch.zeros(2, 320000, device=DEV))
+    net(spec.unsqueeze(1))
+    assert torch.randint(1 << 30, (1,)).item() == after_empty      # identical CPU-generator consumption
