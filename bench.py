@@ -391,6 +391,47 @@ def run_candidate(args, rank, local_rank, world):
             return timed_once(run) / args.steps
         for h2d, d2h in ((True, True), (False, True), (True, False), (False, False)):
             print(f"[e2e diag] h2d={h2d} d2h={d2h}: {variant(h2d, d2h):.3f} ms/step", file=sys.stderr)
+        # same event structure, but only 4 KB cross the bus: separates "bytes" from "stream/event structure"
+        tiny_host = torch.zeros(1024).pin_memory()
+        tiny_dev = torch.zeros(1024, device=dev)
+
+        def upload_tiny(i):
+            k = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(buf_free[k])
+                tiny_dev.copy_(tiny_host, non_blocking=True)
+                h2d_done[k].record(copy_stream)
+
+        def run_tiny():
+            cur = torch.cuda.current_stream()
+            for k in range(2):
+                buf_free[k].record(cur)
+            upload_tiny(0)
+            for i in range(args.steps):
+                k = i & 1
+                if i + 1 < args.steps:
+                    upload_tiny(i + 1)
+                cur.wait_event(h2d_done[k])
+                train_step(dev_bufs[k])
+                buf_free[k].record(cur)
+            torch.cuda.synchronize()
+        print(f"[e2e diag] 4 KB copies, same events: {timed_once(run_tiny) / args.steps:.3f} ms/step", file=sys.stderr)
+
+        # full copies, but issued right AFTER the step's launch instead of before it
+        def run_late():
+            cur = torch.cuda.current_stream()
+            for k in range(2):
+                buf_free[k].record(cur)
+            upload(0)
+            for i in range(args.steps):
+                k = i & 1
+                cur.wait_event(h2d_done[k])
+                train_step(dev_bufs[k])
+                buf_free[k].record(cur)
+                if i + 1 < args.steps:
+                    upload(i + 1)
+            torch.cuda.synchronize()
+        print(f"[e2e diag] full copies issued after the launch: {timed_once(run_late) / args.steps:.3f} ms/step", file=sys.stderr)
 
     # ---- (3) roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every GEMM launch in a
     #          repeat of the timed steps (kept out of the headline timing so the events do not perturb it)
