@@ -256,10 +256,16 @@ def run_candidate(args, rank, local_rank, world):
         graphed = GraphedTrainStep(mel, net, opt, F.binary_cross_entropy_with_logits, dev_waves[0], y,
                                    reducer=reducer, warmup=3)
 
-    def train_step(wave_dev):
+    def train_step(wave_dev, consumed=None):
         # public API: either the eager modules (mel -> net -> loss.backward -> opt.step) or the same step replayed
-        # as one CUDA graph (passt_b200.graphed.GraphedTrainStep; inputs are copied into its static buffers)
-        return graphed(wave_dev, None) if graphed is not None else eager_step(wave_dev)
+        # as one CUDA graph (passt_b200.graphed.GraphedTrainStep; inputs are copied into its static buffers).
+        # consumed: event recorded once the input buffer may be refilled (graph: right after the staging copy)
+        if graphed is not None:
+            return graphed(wave_dev, None, consumed=consumed)
+        loss = eager_step(wave_dev)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())
+        return loss
 
     def barrier():
         if world > 1:
@@ -338,8 +344,7 @@ def run_candidate(args, rank, local_rank, world):
             if i + 1 < steps:
                 upload(i + 1)
             cur.wait_event(h2d_done[k])
-            loss = train_step(dev_bufs[k])
-            buf_free[k].record(cur)
+            loss = train_step(dev_bufs[k], consumed=buf_free[k])
             loss_hosts[k].copy_(loss.detach().reshape(1), non_blocking=True)
             loss_done[k].record(cur)
             if i > 0:

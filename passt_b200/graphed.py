@@ -89,11 +89,27 @@ class GraphedTrainStep:
             self.net._preset_plan = None
         return loss
 
-    def __call__(self, wave: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None):
+    @staticmethod
+    def _stage(dst: torch.Tensor, src: torch.Tensor):
+        """Copy a step input into its static buffer.  Device-resident sources are copied by a kernel, not by
+        cudaMemcpy: a device-to-device memcpy can be queued on the copy engine behind a loader's host-to-device
+        transfer of the *next* batch and then stalls the whole step for the length of that transfer (measured:
+        +1.1 ms per step with an 82 MB prefetch in flight)."""
+        if src.is_cuda and src.dtype == dst.dtype and src.shape == dst.shape:
+            torch.mul(src, 1, out=dst)
+        else:
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self, wave: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None,
+                 consumed: Optional[torch.cuda.Event] = None):
+        """consumed: optional event recorded as soon as the inputs have been copied out of ``wave`` / ``target`` --
+        a prefetching loader may refill those buffers from then on, it does not have to wait for the step."""
         if wave is not None:
-            self.wave.copy_(wave, non_blocking=True)
+            self._stage(self.wave, wave)
         if target is not None:
-            self.target.copy_(target, non_blocking=True)
+            self._stage(self.target, target)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())
         self._host_draws()
         if hasattr(self.opt, "sync_hyperparams"):
             self.opt.sync_hyperparams()       # passt_b200.FusedAdamW: the replayed step reads lr etc. from a pinned mirror
