@@ -54,16 +54,22 @@ def lib_path() -> str:
 
 
 def load():
-    """Load (building first if the .so is absent and nvcc is present). Raises if unavailable."""
+    """Load the library.  build.build() decides from the source digest (lib/build.sha256) whether the .so has to be
+    (re)compiled, so edited .cu sources can never run a stale library; raises if it cannot be built or loaded."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.isfile(_LIB_PATH):
-            from . import build as _build
+        from . import build as _build
+        try:
             _build.build()
+        except Exception:
+            # sources changed (or no .so) and it cannot be rebuilt here: fail loudly rather than run a stale library,
+            # unless the caller explicitly accepts the existing file
+            if not (os.path.isfile(_LIB_PATH) and os.environ.get("PASST_B200_ALLOW_STALE_LIB") == "1"):
+                raise
         lib = C.CDLL(_LIB_PATH)
         for name, (res, args) in _SIGS.items():
             try:

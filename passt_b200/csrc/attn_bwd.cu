@@ -517,12 +517,7 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   p.dq_acc = dq_acc;
   p.dbias = dbias_qkv;
   p.timeline = pb::g_attn_bwd_timeline;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     AttnBwdSmem::kTotal));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal, attn_bwd_kernel);
   const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
   attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tmQKV, tmdO, tmdQKV, tmdQacc, p);
   PB_LAUNCH_CHECK();

@@ -377,12 +377,7 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   p.n_qt = (N + kQTile - 1) / kQTile;
   p.total_items = B * H * p.n_qt;
   p.timeline = pb::g_attn_timeline;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     AttnFwdSmem::kTotal));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(AttnFwdSmem::kTotal, attn_fwd_kernel);
   const int grid = p.total_items < 2 * kNumSMs ? p.total_items : 2 * kNumSMs;
   attn_fwd_kernel<<<grid, kAttnThreads, AttnFwdSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmO, p);
   PB_LAUNCH_CHECK();

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <cstdio>
+#include <atomic>
 
 namespace pb {
 
@@ -25,6 +26,20 @@ constexpr int kNumSMs = 148;
   do {                                          \
     cudaError_t _e = cudaPeekAtLastError();     \
     if (_e != cudaSuccess) { cudaGetLastError(); return (int)_e; } \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: remember which devices of this process have
+// been configured for a kernel (a process-wide `static bool` would leave a second GPU unconfigured and fail at launch).
+#define PB_SET_SMEM_ONCE(bytes, ...)                                                                        \
+  do {                                                                                                      \
+    static std::atomic<unsigned long long> _pb_done{0};                                                     \
+    int _pb_dev = 0;                                                                                        \
+    PB_CUDA_TRY(cudaGetDevice(&_pb_dev));                                                                   \
+    const unsigned long long _pb_bit = 1ull << (_pb_dev & 63);                                              \
+    if (!(_pb_done.load(std::memory_order_relaxed) & _pb_bit)) {                                            \
+      PB_CUDA_TRY(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes))); \
+      _pb_done.fetch_or(_pb_bit, std::memory_order_relaxed);                                                \
+    }                                                                                                       \
   } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -465,12 +465,7 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
     p.lbo_a = g_desc_override.v[0]; p.sbo_a = g_desc_override.v[1]; p.kstep_a = g_desc_override.v[2];
     p.lbo_b = g_desc_override.v[3]; p.sbo_b = g_desc_override.v[4]; p.kstep_b = g_desc_override.v[5];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<BN, MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm_kernel<BN, MODE, BMN>);
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;

@@ -520,12 +520,7 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
     p.lbo_a = g_desc_override.v[0]; p.sbo_a = g_desc_override.v[1]; p.kstep_a = g_desc_override.v[2];
     p.lbo_b = g_desc_override.v[3]; p.sbo_b = g_desc_override.v[4]; p.kstep_b = g_desc_override.v[5];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm2_kernel<MODE, BMN>);
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
   if (clusters <= 0) return 0;

@@ -389,11 +389,7 @@ int passt_mel_forward(const void* workspace, const float* wave, float* out, int 
   p.wave = wave; p.out = out; p.B = B; p.L = L; p.hop = hop;
   p.T = 1 + (L - 1) / hop;
   p.rnd = rnd; p.freqm = freqm; p.timem = timem; p.preemph = 0.97f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmemBytes));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(kMelSmemBytes, mel_kernel);
   dim3 grid((p.T + kFramesPerCta - 1) / kFramesPerCta, B);
   mel_kernel<<<grid, kMelWarps * 32, kMelSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(p, t, bank);
   PB_LAUNCH_CHECK();

@@ -618,11 +618,7 @@ int passt_ln_bwd(const void* dh_bf16, const float* x, const float* mean, const f
   int rows_per_cta = (M + ctas - 1) / ctas;
   if (rows_per_cta < kLnBwdWarps) rows_per_cta = kLnBwdWarps;
   ctas = (M + rows_per_cta - 1) / rows_per_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA_TRY(cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
-    attr_set = true;
-  }
+  PB_SET_SMEM_ONCE(kLnBwdSmem, ln_bwd_kernel);
   ln_bwd_kernel<<<ctas, kLnBwdWarps * 32, kLnBwdSmem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dh_bf16, x, mean, rstd, gamma, g_in, g_out, (__nv_bfloat16*)g_out_bf16, dgamma, dbeta,
       colsum, M, rows_per_cta);

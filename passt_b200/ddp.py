@@ -7,6 +7,13 @@ Here the hand-written backward writes every gradient into ONE flat fp32 buffer i
 tail, then each transformer block from last to first, then the patch-embedding head) the chunk's all-reduce is
 enqueued asynchronously, so the exchange overlaps the remaining backward kernels.  The path shards by batch and
 this is its only collective.
+
+Contract with autograd (checked, not assumed): the backward returns VIEWS of the flat buffer as the parameter
+gradients, and averaging is only correct if ``p.grad`` ends up aliasing that buffer -- i.e. the gradients did not
+exist before the backward (``optimizer.zero_grad(set_to_none=True)``, the torch default).  With a pre-existing
+``.grad`` (``set_to_none=False``, gradient accumulation) AccumulateGrad would add the still un-reduced view into a
+different tensor while NCCL is reducing the flat buffer; ``all_reduce()`` detects that and raises instead of letting
+the replicas diverge silently.
 """
 from __future__ import annotations
 
@@ -24,6 +31,8 @@ class GradAllReducer:
         self.min_chunk = min_chunk_elems
         self._works: List = []
         self._pending = None      # (flat, lo, hi) chunk being coalesced
+        self._net = net
+        self._flat = None         # flat gradient buffer of the backward pass being reduced
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if net is not None:
             net._grad_chunk_hook = self.on_chunk_ready
@@ -32,6 +41,7 @@ class GradAllReducer:
     def on_chunk_ready(self, flat: torch.Tensor, lo: int, hi: int):
         if self.world == 1 or hi <= lo:
             return
+        self._flat = flat
         if self._pending is not None:
             pf, plo, phi = self._pending
             if pf is flat and (hi == plo or lo == phi):
@@ -63,5 +73,26 @@ class GradAllReducer:
             if chunk is not None:
                 chunk.div_(self.world)
         self._works = []
+        if self._net is not None and self._flat is not None:
+            self.check_grads_alias(self._net, self._flat)
+        self._flat = None
+
+    @staticmethod
+    def check_grads_alias(net, flat=None):
+        """Raise unless every parameter gradient of ``net`` lives inside the flat buffer that was all-reduced."""
+        flat = flat if flat is not None else getattr(net, "_last_flat_grad", None)
+        if flat is None:
+            return
+        lo = flat.data_ptr()
+        hi = lo + flat.numel() * flat.element_size()
+        for n, p in net.named_parameters():
+            g = p.grad
+            if g is None:
+                continue
+            if not (lo <= g.data_ptr() < hi):
+                raise RuntimeError(
+                    f"passt_b200.ddp: the gradient of '{n}' does not alias the all-reduced flat buffer, so it holds "
+                    "un-reduced values (a .grad existed before backward: use optimizer.zero_grad(set_to_none=True), "
+                    "and do not accumulate gradients over several backward passes with GradAllReducer)")
 
     finish = all_reduce

@@ -25,7 +25,12 @@ from . import engine
 
 class GraphedTrainStep:
     def __init__(self, mel, net, optimizer, loss_fn: Callable, example_wave: torch.Tensor,
-                 example_target: torch.Tensor, reducer=None, warmup: int = 3):
+                 example_target: torch.Tensor, reducer=None, warmup: int = 3, restore_after_warmup: bool = True):
+        """Building the step runs ``max(1, warmup)`` REAL eager training steps on the example batch (allocator,
+        cudaFuncSetAttribute, bf16 weight cache, optimizer state and pointer tables must exist before capture).
+        With ``restore_after_warmup`` (default) the network parameters and the optimizer state are put back to what
+        they were before those steps (fresh optimizer state is zeroed), so constructing the object has no training
+        side effect; pass False to keep the warm-up updates."""
         if not example_wave.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (sm_100a); there is no CPU path")
         self.mel, self.net, self.opt, self.loss_fn, self.reducer = mel, net, optimizer, loss_fn, reducer
@@ -33,7 +38,6 @@ class GraphedTrainStep:
         self.wave = torch.empty_like(example_wave)
         self.target = torch.empty_like(example_target)
         self.band_dev = torch.zeros(2, dtype=torch.float64, device=dev)
-        self.band_host = torch.zeros(2, dtype=torch.float64).pin_memory()
         self.toff_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         mel.train(); net.train()
         B, Lw = example_wave.shape
@@ -44,6 +48,7 @@ class GraphedTrainStep:
         self.idx_dev = torch.zeros(2, probe.ntok - 2, dtype=torch.int32, device=dev)
         self.graph = None
         self.loss = None
+        snap = self._snapshot() if restore_after_warmup else None
         # eager warm-up on a side stream (allocator, cudaFuncSetAttribute, bf16 weight cache, optimizer state)
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -59,12 +64,60 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         torch.cuda.synchronize()
+        if snap is not None:
+            self._restore(snap)
+
+    # ---- state handling around the warm-up / after a checkpoint load ------------------------------------------
+    def _snapshot(self):
+        params = [p.detach().clone() for p in self.net.parameters()]
+        had_state = len(self.opt.state) > 0
+        opt_state = None
+        if had_state:
+            opt_state = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state[p].items()}
+                         if p in self.opt.state else None
+                         for g in self.opt.param_groups for p in g["params"]]
+        return params, had_state, opt_state
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        params, had_state, opt_state = snap
+        for p, v in zip(self.net.parameters(), params):
+            p.copy_(v)                               # in place: the captured graph keeps the parameter addresses
+        flat = [p for g in self.opt.param_groups for p in g["params"]]
+        for i, p in enumerate(flat):
+            st = self.opt.state.get(p)
+            if not st:
+                continue
+            for k, v in st.items():
+                if not torch.is_tensor(v):
+                    continue
+                old = opt_state[i].get(k) if (had_state and opt_state[i] is not None) else None
+                if old is not None:
+                    v.copy_(old)
+                else:
+                    v.zero_()                         # state created by the warm-up: back to "never stepped"
+        self.resync()
+
+    def resync(self):
+        """Call after the parameters were changed behind the graph's back (``net.load_state_dict``, manual edits):
+        re-casts the bf16 GEMM-operand copies the captured forward reads.  (With FusedAdamW attached the captured
+        forward contains no refresh of its own -- the optimizer pass rewrites the copies -- so without this the first
+        replay after a checkpoint load would run on stale bf16 weights.)"""
+        depth = len(self.net.blocks)
+        P = dict(self.net.named_parameters())
+        wnames = ["patch_embed.proj.weight"] + [f"blocks.{i}.{w}.weight" for i in range(depth)
+                                                for w in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]
+        with torch.cuda.device(self.wave.device):
+            self.net._wcache.refresh_all([P[n] for n in wnames])
 
     # host RNG, in the reference's order: mel band first (preprocess.py:63-64), then the network's draws
     def _host_draws(self):
         fmin, fmax = self.mel.draw_band()
-        self.band_host[0] = float(fmin); self.band_host[1] = float(fmax)
-        self.band_dev.copy_(self.band_host, non_blocking=True)
+        # a FRESH pinned temporary per call (like draw_step_plan's index copies): the caching host allocator keeps the
+        # block alive until the queued copy has run, so a host that runs ahead of the GPU can never overwrite the band
+        # of a step that has not executed yet (a persistent pinned mirror would be torn / reused across steps)
+        self.band_dev.copy_(torch.tensor([float(fmin), float(fmax)], dtype=torch.float64).pin_memory(),
+                            non_blocking=True)
         x_meta = torch.empty(self._x_shape, device="meta")
         plan = engine.draw_step_plan(self.net, _ShapeOnCuda(x_meta, self.wave.device), True, static_idx=self.idx_dev,
                                      static_toff=self.toff_dev)

@@ -44,30 +44,42 @@ class FusedAdamW(torch.optim.Optimizer):
                 total += (p.numel() + 3) // 4 * 4          # keep every moment view 16-byte aligned
             m = torch.zeros(total, device=dev)
             v = torch.zeros(total, device=dev)
-            hyper_host = torch.zeros(8).pin_memory()
             hyper_dev = torch.zeros(8, device=dev)
             for p, o in zip(ps, offs):
                 self.state[p] = dict(step=hyper_dev[5], exp_avg=m[o:o + p.numel()].view_as(p),
                                      exp_avg_sq=v[o:o + p.numel()].view_as(p))
-            self._g.append(dict(tables={}, hyper_host=hyper_host, hyper_dev=hyper_dev, m=m, v=v, offs=offs))
+            self._g.append(dict(tables={}, hyper_dev=hyper_dev, m=m, v=v, offs=offs))
         self.sync_hyperparams()
 
-    # ---- hyper-parameters live in a pinned host mirror; the copy to the device is part of every step (and of a
-    #      captured graph, where it re-reads the mirror at replay time)
+    # ---- hyper-parameters live in device memory (hyper_dev[0:5]; [5] is the step count).  They are pushed with a
+    #      stream-ordered copy from a FRESH pinned temporary per call (the caching host allocator keeps it alive until
+    #      the copy has executed), never from a persistent pinned mirror: a host that runs ahead of the GPU could
+    #      overwrite such a mirror with the lr of step N+k before step N's copy has run.  Eager step() pushes by itself;
+    #      a captured step contains no copy at all -- GraphedTrainStep calls sync_hyperparams() right before each replay.
     def sync_hyperparams(self):
         for group, g in zip(self.param_groups, self._g):
             if g is None:
                 continue
-            h = g["hyper_host"]
-            h[0] = float(group["lr"]); h[1] = float(group["betas"][0]); h[2] = float(group["betas"][1])
-            h[3] = float(group["eps"]); h[4] = float(group["weight_decay"])
+            h = torch.tensor([float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
+                              float(group["eps"]), float(group["weight_decay"])], dtype=torch.float32)
+            dev = g["hyper_dev"].device
+            with torch.cuda.device(dev):
+                g["hyper_dev"][:5].copy_(h.pin_memory(), non_blocking=True)
+
+    @staticmethod
+    def _drop_uncaptured(tables):
+        """Forget pointer tables, EXCEPT those a CUDA graph was captured with: the graph's memcpy node re-reads that
+        pinned host table on every replay, so freeing it would let the pinned allocator hand the block to someone else
+        (e.g. a DataLoader's pin_memory) and the kernel would dereference garbage."""
+        for k in [k for k, e in tables.items() if not e[4]]:
+            tables.pop(k)
 
     def attach(self, net):
         """Let the step also rewrite the bf16 copies of ``net``'s weight matrices (passt_b200.PaSST)."""
         self._net = net
         for g in self._g:
             if g is not None:
-                g["tables"].clear()
+                self._drop_uncaptured(g["tables"])
         return self
 
     def _bf16_copy(self, p):
@@ -121,6 +133,8 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         refreshed = False
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyperparams()
         for group, g in zip(self.param_groups, self._g):
             if g is None:
                 continue
@@ -128,11 +142,8 @@ class FusedAdamW(torch.optim.Optimizer):
             if ent is None:
                 continue
             _, table_dev, blocks, n, _ = ent
-            if not torch.cuda.is_current_stream_capturing():
-                self.sync_hyperparams()
             dev = g["hyper_dev"].device
             with torch.cuda.device(dev):
-                g["hyper_dev"][:5].copy_(g["hyper_host"][:5], non_blocking=True)
                 L.call("passt_adamw_step", L.ptr(table_dev), n, blocks, L.ptr(g["hyper_dev"]), L.stream_ptr())
             refreshed = True
         if refreshed and self._net is not None:
@@ -145,7 +156,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for group, g in zip(self.param_groups, self._g):
             if g is None:
                 continue
-            g["tables"].clear()
+            self._drop_uncaptured(g["tables"])
             for p, o in zip(group["params"], g["offs"]):
                 st = self.state.get(p)
                 if not st:

@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from util import build_net, quiet, relerr
+from util import build_net, grad_metrics, quiet, relerr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -111,9 +111,10 @@ def test_net_forward_backward_parity_depth2(kw, training):
             assert g is None or float(g.abs().max()) == 0.0      # unused in forward (passt.py:582-588)
             continue
         assert g is not None, k
-        e = relerr(g, v.grad)
-        if e > 2e-2:
-            bad.append((k, e))
+        m = grad_metrics(g, v.grad)
+        # north_star bf16 bound (1e-2, max-norm) + element-aware companions (see tests/test_gpu_fulldepth.py)
+        if m["relmax"] > 1e-2 or m["rel_l2"] > 2e-2 or m["cos"] < 0.9995:
+            bad.append((k, m))
     assert not bad, bad
 
 

@@ -57,3 +57,38 @@ def depth2_params(params12, last=11):
         else:
             out[k] = v
     return out
+
+
+def grad_metrics(a, b):
+    """Error metrics of candidate `a` against reference `b` (same shape):
+      relmax  max|a-b| / max|b|                     (the whole-tensor norm north_star's tolerances are stated in)
+      rel_l2  ||a-b||_2 / ||b||_2
+      cos     cosine similarity of the flattened tensors
+      elrel   max over elements with |b| > 1e-3 max|b| of |a-b| / |b|   (element-relative; bf16 noise shows here)
+      elrel50 median of the same ratio
+    A tensor whose small entries are wrong passes `relmax` but not `rel_l2` / `cos`."""
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    d = (a - b).abs()
+    bmax = b.abs().max().item() + 1e-300
+    sel = b.abs() > 1e-3 * bmax
+    ratio = d[sel] / b[sel].abs() if bool(sel.any()) else torch.zeros(1, dtype=torch.float64)
+    return dict(relmax=d.max().item() / bmax, rel_l2=(a - b).norm().item() / (b.norm().item() + 1e-300),
+                cos=float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)), elrel=ratio.max().item(),
+                elrel50=ratio.median().item(), refmax=bmax)
+
+
+def golden_sample_index(n: int, n_samples: int = 4096):
+    return torch.arange(n)[:: max(1, n // n_samples)][:n_samples]
+
+
+def golden_projections(name: str, g, n_proj: int = 4):
+    """Same random projections as tests/golden/make_golden_grads.py (seeded by crc32 of the parameter name)."""
+    import zlib
+    out = []
+    flat = g.detach().double().cpu().flatten()
+    for j in range(n_proj):
+        gen = torch.Generator().manual_seed((zlib.crc32(name.encode()) + j) & 0x7FFFFFFF)
+        r = torch.randn(flat.numel(), generator=gen, dtype=torch.float64)
+        out.append(float(flat @ r))
+    return torch.tensor(out, dtype=torch.float64)
