@@ -109,6 +109,41 @@ int passt_head_bwd(const float* x, const void* delta_bf16, const float* norm_g, 
                    float* d_norm_b, float* d_hln_g, float* d_hln_b, float* dW, float* dbias, float* colsum, int B,
                    int ntok, int C, void* stream);
 
+
+/* ---- losses, SWA, validation post-processing ------------------------------------- */
+/* mean BCE-with-logits against targets mixed on the fly (y*lam + y[perm]*(1-lam); perm/lam NULL = no mixup) and
+ * d loss / d logits in ONE launch (training_step, ex_audioset.py:172-192).  workspace: passt_loss_workspace_bytes(B)
+ * bytes, zero-initialised once by the caller. */
+size_t passt_loss_workspace_bytes(int B);
+int passt_loss_bce(const float* logits, const float* target, const int* perm, const float* lam, float* loss,
+                   float* dlogits, void* workspace, int B, int C, void* stream);
+/* mean of CE(z, y)*lam + CE(z, y[perm])*(1-lam) and its logit gradient (ex_esc50.py:151-169); target: int64 [B] */
+int passt_loss_ce(const float* logits, const long long* target, const int* perm, const float* lam, float* loss,
+                  float* dlogits, void* workspace, int B, int C, void* stream);
+/* out = in * scalar_dev[0]  (backward of the two losses: dlogits times the upstream gradient, no host sync) */
+int passt_scale_dev(float* out, const float* in, const float* scalar_dev, size_t n, void* stream);
+/* validation side: mean logits of K nets and sigmoid (mode 0: sigmoid(mean logits), EnsembelerModel models/passt.py:
+ * 1021-1036 + torch.sigmoid of validation_step ex_audioset.py:236-238; mode 1: mean of sigmoids).  logits_ptrs is a
+ * HOST array of K <= 16 device pointers. */
+int passt_ens_sigmoid(const float* const* logits_ptrs, int K, float* mean_logits, float* prob, size_t n, int mode,
+                      void* stream);
+/* per-class average precision with sklearn's tie handling (validation_epoch_end, ex_audioset.py:262-266) on the
+ * device: scores / targets f32 [n, C], ap f32 [C] (NaN for a class without positives); n <= ~45000 */
+int passt_average_precision(const float* scores, const float* targets, float* ap, int n, int C, void* stream);
+/* SWA running average over a list of tensors in ONE launch (helpers/swa_callback.py:246-268).  table: device array of
+ * 32-byte records {const float* p_model; float* p_swa; uint64_t n; uint32_t first_block; uint32_t pad},
+ * first_block = running sum of ceil(n / 4096); n_averaged == 0 copies. */
+int passt_swa_update(const void* table, int n_entries, int total_blocks, long long n_averaged, void* stream);
+
+/* ---- waveform-side augmentation while staging a batch ------------------------------ */
+/* gain -> pad/truncate to L -> roll -> optional zero-mean waveform mixup with another clip of the batch (+ target
+ * mix), audioset/dataset.py:107-140,315-339.  raw: all source clips (f32); src_off [B] int64 element offsets;
+ * src_len [B]; gain [B] or NULL; shift [B] or NULL; mix_idx [B] (-1 = not mixed) with mix_lam [B], or both NULL;
+ * out [B, L]; tgt / tgt_out [B, C] or both NULL. */
+int passt_wave_augment(const float* raw, const long long* src_off, const int* src_len, const float* gain,
+                       const int* shift, const int* mix_idx, const float* mix_lam, float* out, const float* tgt,
+                       float* tgt_out, int B, int L, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

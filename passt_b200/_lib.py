@@ -40,6 +40,14 @@ _SIGS = {
     "passt_attn_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "passt_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "passt_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
+    "passt_loss_workspace_bytes": (C.c_size_t, [i32]),
+    "passt_loss_bce": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "passt_loss_ce": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "passt_scale_dev": (i32, [vp, vp, vp, C.c_size_t, vp]),
+    "passt_ens_sigmoid": (i32, [vp, i32, vp, vp, C.c_size_t, i32, vp]),
+    "passt_average_precision": (i32, [vp, vp, vp, i32, i32, vp]),
+    "passt_swa_update": (i32, [vp, i32, i32, C.c_longlong, vp]),
+    "passt_wave_augment": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "passt_attn_debug_timeline": (None, [vp]),
     "passt_attn_bwd_debug_timeline": (None, [vp]),
 }
@@ -107,7 +115,7 @@ def check(rc: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"passt_adamw_step": 2, "passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0,
+_LAUNCHES = {"passt_adamw_step": 2, "passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_mel_workspace_bytes": 0, "passt_loss_workspace_bytes": 0,
              "passt_attn_bwd_workspace_bytes": 0}
 _launch_counter = 0
 

@@ -108,9 +108,70 @@ adamw_multi_kernel(const AdamEntry* __restrict__ table, int n_entries, const flo
   }
 }
 
+// Stochastic weight averaging over a list of tensors in one launch (StochasticWeightAveraging.update_parameters /
+// avg_fn, helpers/swa_callback.py:246-268):  p_swa <- p_model                              if n_averaged == 0
+//                                             p_swa <- p_swa + (p_model - p_swa)/(n_averaged+1) otherwise
+// One 32-byte record per tensor: {const float* src = p_model; float* dst = p_swa; uint64 n = elements;
+// uint32 first_block = running sum of ceil(n / 4096); uint32 pad}; 16-byte vector path when n % 4 == 0 and both
+// pointers are 16-byte aligned, scalar path otherwise.
+struct SwaEntry {
+  const float* src;
+  float* dst;
+  unsigned long long n;          // elements
+  unsigned int first_block, pad;
+};
+static_assert(sizeof(SwaEntry) == 32, "SwaEntry layout is part of the C ABI");
+constexpr int kSwaElemsPerBlock = 4096;
+
+__global__ void __launch_bounds__(256)
+swa_multi_kernel(const SwaEntry* __restrict__ table, int n_entries, float inv_np1, int first) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_e = lo;
+  }
+  __syncthreads();
+  const SwaEntry e = table[s_e];
+  const size_t base = size_t(blockIdx.x - e.first_block) * kSwaElemsPerBlock;
+  const bool vec = (e.n % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.src) | reinterpret_cast<uintptr_t>(e.dst)) % 16 == 0);
+  if (vec) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = base + size_t(u * 256 + threadIdx.x) * 4;
+      if (i < e.n) {
+        const float4 m = *reinterpret_cast<const float4*>(e.src + i);
+        float4 a = *reinterpret_cast<const float4*>(e.dst + i);
+        if (first) a = m;
+        else { a.x += (m.x - a.x) * inv_np1; a.y += (m.y - a.y) * inv_np1; a.z += (m.z - a.z) * inv_np1; a.w += (m.w - a.w) * inv_np1; }
+        *reinterpret_cast<float4*>(e.dst + i) = a;
+      }
+    }
+  } else {
+    for (int u = 0; u < 16; ++u) {
+      const size_t i = base + size_t(u * 256 + threadIdx.x);
+      if (i < e.n) e.dst[i] = first ? e.src[i] : e.dst[i] + (e.src[i] - e.dst[i]) * inv_np1;
+    }
+  }
+}
+
 }  // namespace pb
 
 extern "C" {
+
+// table: device array of n_entries 32-byte records {const float* p_model; float* p_swa; uint64 n; uint32 first_block;
+// uint32 pad}, first_block = running sum of ceil(n / 4096); n_averaged = models averaged so far (0: plain copy).
+int passt_swa_update(const void* table, int n_entries, int total_blocks, long long n_averaged, void* stream) {
+  using namespace pb;
+  if (table == nullptr || n_entries <= 0 || total_blocks <= 0 || n_averaged < 0) return PB_ERR_BAD_ARG;
+  swa_multi_kernel<<<total_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const SwaEntry*>(table), n_entries, 1.0f / float(n_averaged + 1), n_averaged == 0 ? 1 : 0);
+  PB_LAUNCH_CHECK();
+  return 0;
+}
 
 // table: device array of n_entries 64-byte records {float* p; const float* g; float* m; float* v; void* w16_or_null;
 // uint64 n; uint32 first_block; uint32 vec; uint64 reserved}; total_blocks = sum of ceil(n / 4096).

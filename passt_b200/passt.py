@@ -342,18 +342,17 @@ def get_model(arch="passt_s_kd_p16_128_ap486", pretrained=True, n_classes=527, i
 
 
 class EnsembelerModel(nn.Module):
-    """Average of several nets' logits (models/passt.py:1021-1036)."""
+    """Average of several nets' logits (models/passt.py:1021-1036).  The nets run on the same spectrogram; the logit
+    average is one fused launch (passt_ens_sigmoid) instead of a chain of adds and a divide."""
 
     def __init__(self, models):
         super().__init__()
         self.models = nn.ModuleList(models)
 
     def forward(self, x):
-        total = None
-        for m in self.models:
-            out, _ = m(x)
-            total = out if total is None else total + out
-        total = total / len(self.models)
+        from .evalpath import _sigmoid_mean
+        outs = [m(x)[0] for m in self.models]
+        _, total = _sigmoid_mean(outs, mode=0, want_mean_logits=True)
         return total, total
 
 
