@@ -144,6 +144,24 @@ int passt_wave_augment(const float* raw, const long long* src_off, const int* sr
                        const int* shift, const int* mix_idx, const float* mix_lam, float* out, const float* tgt,
                        float* tgt_out, int B, int L, int C, void* stream);
 
+/* ---- fp32-parity tier of the forward pass (north_star: 1e-3 vs the fp32 reference) ------------------------------- */
+/* GEMM operands split into bf16 hi/lo parts so that the bf16 tcgen05 GEMM (passt_gemm_bf16, mode 2, fp32 output) over
+ * a 3x longer contraction computes A_hi W_hi + A_hi W_lo + A_lo W_hi in fp32: fp32 [R, C] (row stride ld_in) ->
+ * bf16 [R, 3C]; pattern 0 = [hi|hi|lo] (activations, F.linear inputs models/passt.py:285-289,345,359),
+ * pattern 1 = [hi|lo|hi] (weights). */
+int passt_split3_bf16(const float* in, void* out_bf16, long long R, int C, int ld_in, int pattern, void* stream);
+/* split3(gelu_exact(in)) (models/passt.py:286-287) */
+int passt_gelu_split3(const float* in, void* out_bf16, long long R, int C, void* stream);
+/* residual add + LayerNorm in fp32 with the split operand of the next GEMM as output (models/passt.py:377-380) */
+int passt_ln_fwd_f32tier(const float* x_in, const float* delta_f32, float* x_out, void* h_split_bf16,
+                         const float* gamma, const float* beta, int M, int dim, float eps, void* stream);
+/* passt_im2col with fp32 output rows [B*ntok, 256] (split afterwards) */
+int passt_im2col_f32(const float* mel, float* A_f32, const int* patch_f, const int* patch_t, int B, int ntok, int Fm,
+                     int Tm, int fstride, int tstride, const int* mix_perm, const float* mix_lam, void* stream);
+/* softmax(q k^T * scale) v in fp32 (models/passt.py:345-358): qkv f32 [B, N, 3*H*64] -> split3 of the [B, N, H*64]
+ * attention output */
+int passt_attn_fwd_f32(const float* qkv, void* out_split_bf16, int B, int N, int H, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

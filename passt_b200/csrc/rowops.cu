@@ -204,20 +204,22 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int
 // ------------------------------------------------------------------------------------------------
 // im2col of the kept patches (optionally mixing two clips: x*lam + x[perm]*(1-lam), ex_audioset.py:173-177)
 // ------------------------------------------------------------------------------------------------
+template <bool F32OUT>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ A, const int* __restrict__ patch_f,
+im2col_kernel(const float* __restrict__ mel, void* __restrict__ A, const int* __restrict__ patch_f,
               const int* __restrict__ patch_t, int B, int ntok, int Fm, int Tm, int fstride, int tstride,
               const int* __restrict__ mix_perm, const float* __restrict__ mix_lam) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= B * ntok) return;
   const int b = gw / ntok, n = gw - b * ntok;
-  uint4 o = make_uint4(0, 0, 0, 0);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
   if (n >= 2) {
     const int f0 = patch_f[n - 2] * fstride, t0 = patch_t[n - 2] * tstride;
     const int ky = lane >> 1, kx = (lane & 1) * 8;
     const float* src = mel + (size_t(b) * Fm + f0 + ky) * Tm + t0 + kx;
-    float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __ldg(src + i);
     if (mix_perm) {
@@ -226,10 +228,17 @@ im2col_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ A, cons
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = v[i] * lam + __ldg(src2 + i) * (1.0f - lam);
     }
+  }
+  if (F32OUT) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(A) + size_t(gw) * 256 + lane * 8);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A) + size_t(gw) * 256 + lane * 8) = o;
   }
-  *reinterpret_cast<uint4*>(A + size_t(gw) * 256 + lane * 8) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,8 +655,21 @@ int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* 
   if (B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
   const long long warps = (long long)B * ntok;
   const int blocks = int((warps * 32 + 255) / 256);
-  im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, (__nv_bfloat16*)A_bf16, patch_f, patch_t, B, ntok,
-                                                          Fm, Tm, fstride, tstride, mix_perm, mix_lam);
+  im2col_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, A_bf16, patch_f, patch_t, B, ntok, Fm, Tm,
+                                                                 fstride, tstride, mix_perm, mix_lam);
+  PB_LAUNCH_CHECK();
+  return 0;
+}
+
+// same gather with fp32 output rows [B*ntok, 256] (fp32-parity tier: the rows are split into bf16 hi/lo afterwards)
+int passt_im2col_f32(const float* mel, float* A_f32, const int* patch_f, const int* patch_t, int B, int ntok, int Fm,
+                     int Tm, int fstride, int tstride, const int* mix_perm, const float* mix_lam, void* stream) {
+  using namespace pb;
+  if (B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
+  const long long warps = (long long)B * ntok;
+  const int blocks = int((warps * 32 + 255) / 256);
+  im2col_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, A_f32, patch_f, patch_t, B, ntok, Fm, Tm, fstride,
+                                                                tstride, mix_perm, mix_lam);
   PB_LAUNCH_CHECK();
   return 0;
 }

@@ -100,10 +100,21 @@ class WeightCache:
 
     def __init__(self):
         self._store: Dict[tuple, tuple] = {}
-        self.dirty = False
+        self.gen = 0              # bumped whenever the parameters may have changed (dirty <- True)
+        self._dirty = False
         # set by passt_b200.optim.FusedAdamW after a step that rewrote the bf16 copies itself: the next forward skips
         # its own refresh once
         self.fresh_from_optimizer = False
+
+    @property
+    def dirty(self) -> bool:
+        return self._dirty
+
+    @dirty.setter
+    def dirty(self, v: bool):
+        self._dirty = bool(v)
+        if v:
+            self.gen += 1
 
     def get(self, p: torch.Tensor, need_t: bool, force: bool = False):
         key = (p.data_ptr(), tuple(p.shape))
@@ -159,13 +170,15 @@ class WeightCache:
 
     def clear(self):
         self._store.clear()
-        self.dirty = False
+        self._dirty = False
+        self.gen += 1
         self._table_sig = None
 
     def invalidate(self):
         """Force a refresh on next use (parameters were updated without Python seeing it, e.g. by a graph replay)."""
         for k, (ver, wb, wt) in list(self._store.items()):
             self._store[k] = (None, wb, wt)
+        self.gen += 1
 
 
 B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMajorKN)
@@ -216,6 +229,101 @@ def param_names(depth: int) -> List[str]:
     return names + PARAM_ORDER_TAIL
 
 
+class SplitWeightCache:
+    """fp32-parity tier: [out, 3*in] bf16 operands [W_hi | W_lo | W_hi] of the fp32 master weights, rebuilt when a
+    parameter's version changed or the bf16 cache was marked dirty by a training step."""
+
+    def __init__(self):
+        self._store: Dict[tuple, tuple] = {}
+        self.gen = -1             # WeightCache.gen the split operands were last rebuilt at
+
+    def get(self, p: torch.Tensor, force: bool):
+        key = (p.data_ptr(), tuple(p.shape))
+        ent = self._store.get(key)
+        ver = (p.data_ptr(), p._version)
+        if not force and ent is not None and ent[0] == ver:
+            return ent[1]
+        w2 = p.detach().reshape(p.shape[0], -1)
+        R, C = w2.shape
+        ws = ent[1] if ent is not None and ent[1].device == p.device else torch.empty(R, 3 * C, dtype=BF16, device=p.device)
+        L.call("passt_split3_bf16", L.ptr(w2), L.ptr(ws), R, C, C, 1, L.stream_ptr())
+        self._store[key] = (ver, ws)
+        return ws
+
+
+def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P):
+    """fp32-parity forward (north_star 1e-3 tier; eval / no-grad only): every GEMM runs on the tcgen05 bf16 tensor cores
+    over hi/lo-split operands with a 3x longer contraction and fp32 output (csrc/fp32tier.cu), LayerNorm / GELU /
+    attention / residual stream in fp32."""
+    dev = x32.device
+    depth, Dm, H = len(net.blocks), net.embed_dim, net.num_heads
+    hidden = P["blocks.0.mlp.fc1.weight"].shape[0] if depth else 4 * Dm
+    B, ntok = plan.B, plan.ntok
+    M = B * ntok
+    Fg, Tg = net.patch_embed.grid_size
+    fs, ts = net.stride
+    st = L.stream_ptr()
+    f32 = dict(device=dev, dtype=torch.float32)
+    b16 = dict(device=dev, dtype=BF16)
+    sw = getattr(net, "_wsplit", None)
+    if sw is None:
+        sw = net._wsplit = SplitWeightCache()
+    refresh = sw.gen != net._wcache.gen      # a training step / graph replay / optimizer pass happened since
+    sw.gen = net._wcache.gen
+
+    def gemm_f32(As, Ws, out, tab, period, N, K3):
+        _gemm(As, Ws, out, aux=tab, M=M, N=N, K=K3, lda=K3, ldb=K3, ldc=N, mode=2, period=period, ld_aux=N)
+
+    mix_perm, mix_lam = mix if mix is not None else (None, None)
+    A0 = torch.empty(M, 256, **f32)
+    L.call("passt_im2col_f32", L.ptr(x32), L.ptr(A0), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, plan.Fm, plan.Tm,
+           fs, ts, L.ptr(mix_perm), L.ptr(mix_lam), st)
+    A0s = torch.empty(M, 768, **b16)
+    L.call("passt_split3_bf16", L.ptr(A0), L.ptr(A0s), M, 256, 256, 0, st)
+    tab = torch.empty(ntok, Dm, **f32)
+    L.call("passt_token_table", L.ptr(tab), L.ptr(P["cls_token"]), L.ptr(P["dist_token"]), L.ptr(P["new_pos_embed"]),
+           L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]), L.ptr(P["freq_new_pos_embed"]),
+           L.ptr(plan.patch_f), L.ptr(plan.patch_t), ntok, Fg, Tg, plan.toffset, L.ptr(plan.toffset_dev), st)
+    xcur = torch.empty(M, Dm, **f32)
+    gemm_f32(A0s, sw.get(P["patch_embed.proj.weight"], refresh), xcur, tab, ntok, Dm, 768)
+    delta = None
+    scale = float((Dm // H) ** -0.5)
+    for i in range(depth):
+        pre = f"blocks.{i}."
+        h1 = torch.empty(M, 3 * Dm, **b16)
+        x_in = xcur if delta is None else torch.empty(M, Dm, **f32)
+        L.call("passt_ln_fwd_f32tier", L.ptr(xcur), L.ptr(delta), None if delta is None else L.ptr(x_in), L.ptr(h1),
+               L.ptr(P[pre + "norm1.weight"]), L.ptr(P[pre + "norm1.bias"]), M, Dm, 1e-6, st)
+        qkv = torch.empty(M, 3 * Dm, **f32)
+        gemm_f32(h1, sw.get(P[pre + "attn.qkv.weight"], refresh), qkv, P[pre + "attn.qkv.bias"], 1, 3 * Dm, 3 * Dm)
+        att = torch.empty(M, 3 * Dm, **b16)
+        L.call("passt_attn_fwd_f32", L.ptr(qkv), L.ptr(att), B, ntok, H, scale, st)
+        oproj = torch.empty(M, Dm, **f32)
+        gemm_f32(att, sw.get(P[pre + "attn.proj.weight"], refresh), oproj, P[pre + "attn.proj.bias"], 1, Dm, 3 * Dm)
+        x_mid = torch.empty(M, Dm, **f32)
+        h2 = torch.empty(M, 3 * Dm, **b16)
+        L.call("passt_ln_fwd_f32tier", L.ptr(x_in), L.ptr(oproj), L.ptr(x_mid), L.ptr(h2),
+               L.ptr(P[pre + "norm2.weight"]), L.ptr(P[pre + "norm2.bias"]), M, Dm, 1e-6, st)
+        pre_act = torch.empty(M, hidden, **f32)
+        gemm_f32(h2, sw.get(P[pre + "mlp.fc1.weight"], refresh), pre_act, P[pre + "mlp.fc1.bias"], 1, hidden, 3 * Dm)
+        act = torch.empty(M, 3 * hidden, **b16)
+        L.call("passt_gelu_split3", L.ptr(pre_act), L.ptr(act), M, hidden, st)
+        ofc2 = torch.empty(M, Dm, **f32)
+        gemm_f32(act, sw.get(P[pre + "mlp.fc2.weight"], refresh), ofc2, P[pre + "mlp.fc2.bias"], 1, Dm, 3 * hidden)
+        xcur, delta = x_mid, ofc2
+    if delta is not None:
+        x_fin = torch.empty(M, Dm, **f32)
+        L.call("passt_ln_fwd_f32tier", L.ptr(xcur), L.ptr(delta), L.ptr(x_fin), None, None, None, M, Dm, 1e-6, st)
+        xcur = x_fin
+    C = P["head.1.weight"].shape[0]
+    logits = torch.empty(B, C, **f32)
+    feats = torch.empty(B, Dm, **f32)
+    L.call("passt_head_fwd", L.ptr(xcur), None, L.ptr(P["norm.weight"]), L.ptr(P["norm.bias"]),
+           L.ptr(P["head.0.weight"]), L.ptr(P["head.0.bias"]), L.ptr(P["head.1.weight"]), L.ptr(P["head.1.bias"]),
+           L.ptr(logits), L.ptr(feats), None, B, ntok, C, st)
+    return logits, feats
+
+
 class PasstFunction(torch.autograd.Function):
     """(mel image, *params) -> (logits, features).  Saves bf16 activations for the hand-written backward."""
 
@@ -247,6 +355,14 @@ class PasstFunction(torch.autograd.Function):
         x32 = x32.contiguous()
         if x32.shape[1] != 1:
             raise RuntimeError("passt_b200 supports in_channels == 1 (mono spectrograms)")
+        if getattr(net, "precision", "bf16") == "fp32":
+            if need_grad:
+                raise RuntimeError("passt_b200: the fp32-parity tier (net.precision = 'fp32') is forward-only; run it "
+                                   "under torch.no_grad() / on parameters that do not require grad, or train in the bf16 tier")
+            wc.dirty = refresh          # the bf16 copies were NOT refreshed by this call: leave their flag as it was
+            if refresh:
+                wc.gen -= 1             # (re-setting the flag must not count as a new parameter generation)
+            return _forward_fp32_tier(x32, net, plan, mix, P)
         f32 = dict(device=dev, dtype=torch.float32)
         b16 = dict(device=dev, dtype=BF16)
 

@@ -25,12 +25,17 @@ from . import engine
 
 class GraphedTrainStep:
     def __init__(self, mel, net, optimizer, loss_fn: Callable, example_wave: torch.Tensor,
-                 example_target: torch.Tensor, reducer=None, warmup: int = 3, restore_after_warmup: bool = True):
+                 example_target: torch.Tensor, reducer=None, warmup: int = 3, restore_after_warmup: bool = True,
+                 mixup_alpha: Optional[float] = None):
         """Building the step runs ``max(1, warmup)`` REAL eager training steps on the example batch (allocator,
         cudaFuncSetAttribute, bf16 weight cache, optimizer state and pointer tables must exist before capture).
         With ``restore_after_warmup`` (default) the network parameters and the optimizer state are put back to what
         they were before those steps (fresh optimizer state is zeroed), so constructing the object has no training
-        side effect; pass False to keep the warm-up updates."""
+        side effect; pass False to keep the warm-up updates.
+        ``mixup_alpha``: spectrogram mixup of the reference's training_step (ex_audioset.py:172-177) -- the permutation
+        and the lambdas are drawn per step on the host (helpers/mixup.py order: after the mel draws, before the
+        network's), written into static device buffers, folded into the patch gather (PaSST.fused_mixup) and passed
+        to ``loss_fn(logits, target, perm, lam)`` (passt_b200.loss.bce_with_logits / cross_entropy mix the targets)."""
         if not example_wave.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (sm_100a); there is no CPU path")
         self.mel, self.net, self.opt, self.loss_fn, self.reducer = mel, net, optimizer, loss_fn, reducer
@@ -41,6 +46,9 @@ class GraphedTrainStep:
         self.toff_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         mel.train(); net.train()
         B, Lw = example_wave.shape
+        self.mixup_alpha = mixup_alpha
+        self.perm_dev = torch.zeros(B, dtype=torch.int32, device=dev) if mixup_alpha else None
+        self.lam_dev = torch.ones(B, dtype=torch.float32, device=dev) if mixup_alpha else None
         T = 1 + (Lw - 1) // mel.hopsize
         self._x_shape = (B, 1, mel.n_mels, T)
         # static index buffer sized from one trial plan
@@ -118,6 +126,11 @@ class GraphedTrainStep:
         # of a step that has not executed yet (a persistent pinned mirror would be torn / reused across steps)
         self.band_dev.copy_(torch.tensor([float(fmin), float(fmax)], dtype=torch.float64).pin_memory(),
                             non_blocking=True)
+        if self.mixup_alpha:
+            from .loss import draw_mixup
+            perm, lam = draw_mixup(self._x_shape[0], self.mixup_alpha)
+            self.perm_dev.copy_(perm.to(torch.int32).pin_memory(), non_blocking=True)
+            self.lam_dev.copy_(lam.pin_memory(), non_blocking=True)
         x_meta = torch.empty(self._x_shape, device="meta")
         plan = engine.draw_step_plan(self.net, _ShapeOnCuda(x_meta, self.wave.device), True, static_idx=self.idx_dev,
                                      static_toff=self.toff_dev)
@@ -130,8 +143,13 @@ class GraphedTrainStep:
         try:
             with torch.no_grad():
                 spec = self.mel(self.wave, band=self._band).unsqueeze(1)
-            logits, _ = self.net(spec)
-            loss = self.loss_fn(logits, self.target)
+            if self.mixup_alpha:
+                self.net.fused_mixup(self.perm_dev, self.lam_dev)
+                logits, _ = self.net(spec)
+                loss = self.loss_fn(logits, self.target, self.perm_dev, self.lam_dev)
+            else:
+                logits, _ = self.net(spec)
+                loss = self.loss_fn(logits, self.target)
             self.opt.zero_grad(set_to_none=True)
             loss.backward()
             if self.reducer is not None:
@@ -169,6 +187,61 @@ class GraphedTrainStep:
         self.graph.replay()
         self.net._wcache.dirty = True     # the replay updated the parameters: the next eager forward must re-cast
         return self.loss
+
+
+class GraphedInference:
+    """CUDA-graph replay of the inference path (waveform -> mel (eval) -> PaSST forward): ~110 launches become one.
+    ``logits = step(wave)``; the returned tensor is the graph's static output buffer (valid until the next call)."""
+
+    def __init__(self, mel, net, example_wave: torch.Tensor, warmup: int = 2):
+        if not example_wave.is_cuda:
+            raise RuntimeError("GraphedInference needs CUDA tensors (sm_100a); there is no CPU path")
+        self.mel, self.net = mel, net
+        mel.eval(); net.eval()
+        self.wave = torch.empty_like(example_wave)
+        dev = example_wave.device
+        B, Lw = example_wave.shape
+        x_shape = (B, 1, mel.n_mels, 1 + (Lw - 1) // mel.hopsize)
+        # the (deterministic) eval token plan lives in static device buffers: a plan drawn inside the capture would leave
+        # a memcpy node that re-reads a pinned temporary long after it was freed
+        probe = engine.draw_step_plan(net, _ShapeOnCuda(torch.empty(x_shape, device="meta"), dev), False)
+        self.idx_dev = torch.zeros(2, probe.ntok - 2, dtype=torch.int32, device=dev)
+        self.toff_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._plan = engine.draw_step_plan(net, _ShapeOnCuda(torch.empty(x_shape, device="meta"), dev), False,
+                                           static_idx=self.idx_dev, static_toff=self.toff_dev)
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream(device=example_wave.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.wave.copy_(example_wave)
+            for _ in range(max(1, warmup)):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits, self.features = self._body()
+        torch.cuda.synchronize()
+
+    def _body(self):
+        with torch.no_grad():
+            # eval: the band is fixed and no patchout / offset draws reach the kernels, but the two CPU randint draws of
+            # the reference's mel forward (preprocess.py:63-64) are still consumed -- per replay, in __call__
+            spec = self.mel(self.wave, band=(self.mel.fmin, self.mel.fmax)).unsqueeze(1)
+            self.net._preset_plan = self._plan
+            try:
+                return self.net(spec)
+            finally:
+                self.net._preset_plan = None
+
+    def __call__(self, wave: Optional[torch.Tensor] = None, consumed: Optional[torch.cuda.Event] = None):
+        if wave is not None:
+            GraphedTrainStep._stage(self.wave, wave)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())
+        self.mel.draw_band()                 # same CPU-generator consumption as an eager eval forward
+        self.graph.replay()
+        return self.logits
 
 
 class _ShapeOnCuda:

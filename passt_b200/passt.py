@@ -155,6 +155,9 @@ class PaSST(nn.Module):
                                   nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity())
         self.head_dist = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
         self.default_cfg = {}
+        # arithmetic tier of forward(): "bf16" (tensor-core operands rounded to bf16, 1e-2 parity, training + inference)
+        # or "fp32" (hi/lo-split tensor-core GEMMs + fp32 attention, 1e-3 parity, forward-only)
+        self.precision = "bf16"
         self._wcache = engine.WeightCache()
         self._mix = None          # optional (perm[B] int32, lam[B] f32) set by fused_mixup()
         self._preset_plan = None  # optional StepPlan prepared by the caller (CUDA-graph replays)
@@ -199,6 +202,8 @@ class PaSST(nn.Module):
         for k, v in self.__dict__.items():
             if k == "_wcache":
                 new.__dict__[k] = engine.WeightCache()
+            elif k == "_wsplit":
+                continue
             elif k in ("last_plan", "_mix", "_preset_plan"):
                 new.__dict__[k] = None
             else:

@@ -165,3 +165,35 @@ def test_golden_fixture_logits():
         logits, feats = net(x.to(DEV))
     assert relerr(logits, G["eval_logits"]) < 1e-2
     assert relerr(feats, G["eval_features"]) < 1e-2
+
+
+def test_cfg1_fp32_tier_logit_parity_1e3():
+    """BASELINE config 1 at north_star's fp32 tolerance: passt_s_swa_p16_128_ap476, batch 2, 10 s clips, waveform in,
+    net.precision = "fp32" (hi/lo-split tcgen05 GEMMs + fp32 attention): logits / features within 1e-3 (max-norm) of the
+    fp32 CPU oracle, and an order of magnitude closer than the bf16 tier on the same input."""
+    O = _oracle()
+    from passt_b200.preprocess import AugmentMelSTFT
+    cfg = O.NetCfg()
+    params = O.synth_params(cfg, seed=1)
+    net = build_net(cfg, params, DEV).eval()
+    with quiet():
+        mel = AugmentMelSTFT(fmin_aug_range=10, fmax_aug_range=2000).to(DEV).eval()
+    torch.manual_seed(2)
+    wave = 0.1 * torch.randn(2, 320000)
+    mcfg = O.MelCfg()
+    d = O.StepDraws(fmin=mcfg.fmin, fmax=mcfg.resolved_fmax())
+    with torch.no_grad():
+        m = O.mel_frontend(wave, mcfg, d, False).unsqueeze(1)
+        ref_logits, ref_feats = O.passt_forward(params, m, cfg, O.StepDraws())
+        spec = mel(wave.to(DEV)).unsqueeze(1)
+        lb, fb = net(spec)
+        net.precision = "fp32"
+        lf, ff = net(spec)
+    e_bf16, e_fp32 = relerr(lb, ref_logits), relerr(lf, ref_logits)
+    print(f"cfg1 logits relerr: bf16 tier {e_bf16:.2e}, fp32 tier {e_fp32:.2e}; features {relerr(ff, ref_feats):.2e}")
+    assert e_fp32 < 1e-3 and relerr(ff, ref_feats) < 1e-3
+    assert e_bf16 < 1e-2
+    # the fp32 tier refuses to train instead of silently dropping precision guarantees
+    net.train()
+    with pytest.raises(RuntimeError, match="forward-only"):
+        net(spec)
