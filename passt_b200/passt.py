@@ -224,6 +224,11 @@ class PaSST(nn.Module):
         else:
             self._mix = (perm.to(torch.int32).contiguous(), lam.to(torch.float32).contiguous())
 
+    # The whole network is ONE opaque autograd node (engine.PasstFunction) around C-ABI launches, preceded by host-side
+    # RNG draws: there is nothing for a tracing compiler to fuse.  ``torch.compile(self.net)`` -- the reference's default
+    # (compile=True, ex_audioset.py:79,132-135) -- must therefore see the forward as an opaque call: dynamo skips it and
+    # runs it eagerly, gradients flow through the same autograd node (tests/test_gpu_boundary.py).
+    @torch.compiler.disable
     def forward(self, x):
         if x.dim() != 4:
             raise ValueError(f"expected [B, 1, F, T], got {tuple(x.shape)}")

@@ -69,6 +69,7 @@ class AugmentMelSTFT(nn.Module):
             return self.fmin + r0, self.fmax + self.fmax_aug_range // 2 - r1
         return self.fmin, self.fmax
 
+    @torch.compiler.disable
     def forward(self, x, band=None):
         """band: optional (fmin, fmax) drawn by the caller with draw_band() (CUDA-graph replays draw on the host and
         pass the values through a device buffer); None = draw here, like the reference."""
