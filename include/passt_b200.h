@@ -60,6 +60,20 @@ size_t passt_attn_bwd_workspace_bytes(int B, int N, int H);
 int passt_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
                    float* d_bias_qkv, void* workspace, int B, int N, int H, float scale, void* stream);
 
+/* D-fusion: zero the workspace ahead of time, let the GEMM that produces d_out (passt_gemm_bf16 mode 5, kRowDotBf16)
+ * accumulate D = rowsum(d_out o out) into passt_attn_bwd_dsum_ptr(workspace), then call passt_attn_bwd_ex with flags = 1
+ * (no memset, no D pre-pass).  flags = 0 is passt_attn_bwd. */
+int passt_attn_bwd_prepare(void* workspace, int B, int N, int H, void* stream);
+float* passt_attn_bwd_dsum_ptr(void* workspace, int B, int N, int H);
+int passt_attn_bwd_ex(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
+                      float* d_bias_qkv, void* workspace, int B, int N, int H, float scale, int flags, void* stream);
+/* forward schedule: 2 (default) = ping-pong kernel, one CTA per SM with two query tiles in flight (attn_fwd2.cu);
+ * 1 = two CTAs per SM, one query tile each (attn_fwd.cu).  Same results. */
+void passt_attn_fwd_set_variant(int variant);
+/* programmatic dependent launch of the hot-path kernels (1 = default; environment PASST_B200_PDL=0 turns it off) */
+void passt_set_pdl(int enable);
+int passt_get_pdl(void);
+
 /* ---- row kernels ------------------------------------------------------------------------------------------------ */
 /* x_out = x_in (+ delta); h = LayerNorm(x_out) (Block residual + norm1/norm2, models/passt.py:377-380) */
 int passt_ln_fwd(const float* x_in, const void* delta_bf16, float* x_out, void* h_bf16, float* mean, float* rstd,

@@ -123,6 +123,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
   // P^T (bf16 pairs) for query half hc lives at tS + 64*hc .. +32, dS^T at tdP + 64*hc .. +32: each compute warp
@@ -399,6 +400,7 @@ long long* g_attn_bwd_timeline = nullptr;
 __global__ void __launch_bounds__(256)
 attn_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, float* __restrict__ Dsum,
                  int B, int N, int H, int Npad) {
+  pdl_gate();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * N) return;
   const int b = gw / N, n = gw - b * N;
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(256)
 attn_dq_pack_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
                     int rows, int C, float scale, int rows_per_cta) {
   __shared__ float red[8][256];
+  pdl_gate();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
@@ -477,8 +480,32 @@ size_t passt_attn_bwd_workspace_bytes(int B, int N, int H) {
 
 // qkv bf16 [B,N,3C], o bf16 [B,N,C], dO bf16 [B,N,C], lse fp32 [B,H,Npad] (log2 domain, from passt_attn_fwd)
 // -> dqkv bf16 [B,N,3C]; dbias_qkv (optional, fp32 [3C]) += column sums of dqkv (the qkv Linear's bias gradient)
+// D-fusion support: zero the workspace (dQ accumulator + padded D) ahead of time and hand out the D buffer, so that the
+// GEMM that produces dO (mode kRowDotBf16) can accumulate D = rowsum(dO o O) in its epilogue; then call
+// passt_attn_bwd_ex with flags = 1 (workspace prepared, D already accumulated: no memset, no D pre-pass).
+int passt_attn_bwd_prepare(void* workspace, int B, int N, int H, void* stream) {
+  using namespace pb;
+  if (B <= 0 || N <= 0 || H <= 0 || !workspace) return PB_ERR_BAD_ARG;
+  const int C = H * kBHd;
+  const int Npad = ((N + kTile - 1) / kTile) * kTile;
+  PB_CUDA_TRY(cudaMemsetAsync(workspace, 0, size_t(B) * N * C * 4 + size_t(B) * H * Npad * 4,
+                              reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+float* passt_attn_bwd_dsum_ptr(void* workspace, int B, int N, int H) {
+  return reinterpret_cast<float*>(workspace) + size_t(B) * N * H * pb::kBHd;
+}
+
+int passt_attn_bwd_ex(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, float* dbias_qkv,
+                      void* workspace, int B, int N, int H, float scale, int flags, void* stream);
+
 int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, float* dbias_qkv,
                    void* workspace, int B, int N, int H, float scale, void* stream) {
+  return passt_attn_bwd_ex(qkv, o, dO, lse, dqkv, dbias_qkv, workspace, B, N, H, scale, 0, stream);
+}
+
+int passt_attn_bwd_ex(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, float* dbias_qkv,
+                      void* workspace, int B, int N, int H, float scale, int flags, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0 || !workspace) return PB_ERR_BAD_ARG;
   if (dbias_qkv != nullptr && H * kBHd != 768) return PB_ERR_BAD_ARG;   // per-CTA bias partials are sized for C = 768
@@ -488,12 +515,11 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   float* Dsum = dq_acc + size_t(B) * N * C;
   const int Npad = ((N + kTile - 1) / kTile) * kTile;
   // one memset covers dq_acc and the padded D buffer (pad rows of D must be finite: 0 * NaN would poison dS)
-  PB_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, size_t(B) * N * C * 4 + size_t(B) * H * Npad * 4, st));
-  {
+  if (!(flags & 1)) {
+    PB_CUDA_TRY(cudaMemsetAsync(dq_acc, 0, size_t(B) * N * C * 4 + size_t(B) * H * Npad * 4, st));
     const long long warps = (long long)B * N;
-    attn_dsum_kernel<<<int((warps * 32 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o,
-                                                                    (const __nv_bfloat16*)dO, Dsum, B, N, H, Npad);
-    PB_LAUNCH_CHECK();
+    PB_LAUNCH(attn_dsum_kernel, int((warps * 32 + 255) / 256), 256, 0, st, (const __nv_bfloat16*)o,
+              (const __nv_bfloat16*)dO, Dsum, B, N, H, Npad);
   }
   CUtensorMap tmQKV, tmdO, tmdQKV, tmdQacc;
   int rc;
@@ -519,8 +545,7 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
   p.timeline = pb::g_attn_bwd_timeline;
   PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal, attn_bwd_kernel);
   const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
-  attn_bwd_kernel<<<grid, kBwdThreads, AttnBwdSmem::kTotal, st>>>(tmQKV, tmdO, tmdQKV, tmdQacc, p);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal, st, tmQKV, tmdO, tmdQKV, tmdQacc, p);
   {
     if (C % 256 != 0) return PB_ERR_BAD_ARG;
     const int rows = B * N;
@@ -529,9 +554,8 @@ int passt_attn_bwd(const void* qkv, const void* o, const void* dO, const float* 
     int rows_per_cta = (rows + row_blocks - 1) / row_blocks;
     if (rows_per_cta < 8) rows_per_cta = 8;
     row_blocks = (rows + rows_per_cta - 1) / rows_per_cta;
-    attn_dq_pack_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, dbias_qkv, rows, C,
-                                                                      scale, rows_per_cta);
-    PB_LAUNCH_CHECK();
+    PB_LAUNCH(attn_dq_pack_kernel, dim3(col_blocks, row_blocks), 256, 0, st, dq_acc, (__nv_bfloat16*)dqkv, dbias_qkv,
+              rows, C, scale, rows_per_cta);
   }
   return 0;
 }

@@ -18,6 +18,7 @@
 // (exactness is preserved in every case; bf16/fp32 have the exponent range for the lag).
 // TMEM columns: S [0,128)  P [128,192)  O [192,256) -> 256 allocated, two CTAs co-reside per SM.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pb {
 
@@ -89,6 +90,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();
   const uint32_t tmem_S = tmem_base;         // fp32 scores, 128 columns
   const uint32_t tmem_P = tmem_base + 128;   // bf16 probabilities (pairs), 64 columns
   const uint32_t tmem_O = tmem_base + 192;   // fp32 output accumulator, 64 columns
@@ -352,17 +354,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 long long* g_attn_timeline = nullptr;
 
+// attn_fwd2.cu: ping-pong variant (one CTA per SM, two query tiles in flight)
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st);
+int g_attn_fwd_variant = [] {
+  const char* e = getenv("PASST_B200_ATTN_FWD");     // 2 (default): ping-pong kernel; 1: two-CTAs-per-SM kernel
+  return (e != nullptr && e[0] == '1') ? 1 : 2;
+}();
+
 }  // namespace pb
 
 extern "C" {
 // bring-up: device buffer of >= 3*512 int64 receiving clock64 stamps of CTA 0 (NULL disables)
 void passt_attn_debug_timeline(void* buf) { pb::g_attn_timeline = reinterpret_cast<long long*>(buf); }
 
+// 2 (default): ping-pong kernel (attn_fwd2.cu); 1: the two-CTAs-per-SM kernel of this file
+void passt_attn_fwd_set_variant(int v) { pb::g_attn_fwd_variant = (v == 1) ? 1 : 2; }
+
 
 // qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, Npad], Npad = 128*ceil(N/128), log2 domain
 int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0) return PB_ERR_BAD_ARG;
+  if (g_attn_fwd_variant == 2 && g_attn_timeline == nullptr)
+    return launch_attn_fwd2(qkv, out, lse, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
   const int C = H * kHd;
   CUtensorMap tmQKV, tmO;
   int rc;
@@ -379,8 +393,7 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   p.timeline = pb::g_attn_timeline;
   PB_SET_SMEM_ONCE(AttnFwdSmem::kTotal, attn_fwd_kernel);
   const int grid = p.total_items < 2 * kNumSMs ? p.total_items : 2 * kNumSMs;
-  attn_fwd_kernel<<<grid, kAttnThreads, AttnFwdSmem::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQKV, tmO, p);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(attn_fwd_kernel, grid, kAttnThreads, AttnFwdSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmO, p);
   return 0;
 }
 

@@ -47,6 +47,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every hot-path kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and calls pdl_gate() after its on-chip prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) and BEFORE its first global-memory access: griddepcontrol.wait blocks until the
+// preceding kernel of the stream has completed and flushed, launch_dependents then lets the NEXT kernel's CTAs be
+// scheduled (and run their own prologue) as this kernel's CTAs drain.  Chain depth is 1 by construction (the trigger
+// comes after the wait), so at most one successor is ever resident early.  Without the launch attribute both
+// instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_gate() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -318,6 +332,31 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+
+// ---------------------------------------------------------------------------------------------
+// host: kernel launch with the PDL attribute (passt_set_pdl(0) turns it off: plain stream-ordered launches)
+// ---------------------------------------------------------------------------------------------
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define PB_LAUNCH(kernel, grid, block, smem, st, ...)                                        \
+  do {                                                                                       \
+    cudaError_t _le = pb::launch_k(kernel, dim3(grid), dim3(block), size_t(smem), st, __VA_ARGS__); \
+    if (_le != cudaSuccess) { cudaGetLastError(); return (int)_le; }                          \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // host: tensor-map encode through the driver entry point (no link-time libcuda dependency)

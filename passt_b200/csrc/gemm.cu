@@ -16,6 +16,7 @@
 //   "WG" mode  : A[Kt,M] and B[Kt,N] are MN-major (K = tokens) -> D[M,N] = A^T * B       (wgrad), split-K with
 //                fp32 TMA reduce-add into the gradient buffer.
 #include "gemm_defs.cuh"
+#include <cstdlib>
 #include <cstdio>
 #include <mutex>
 
@@ -138,6 +139,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();   // everything above is on-chip; global memory is first touched below
 
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
@@ -393,6 +395,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // host launcher
 // ---------------------------------------------------------------------------------------------
 DescOverride g_desc_override;
+int g_pdl_enabled = [] {
+  const char* e = getenv("PASST_B200_PDL");      // default on; PASST_B200_PDL=0 or passt_set_pdl(0): plain launches
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}();
 static int g_use_2cta = 1;   // passt_gemm_set_2cta(): bring-up / A-B switch between the 1-CTA and 2-CTA kernels
 
 template <int BN, int MODE, bool BMN = false>
@@ -470,8 +476,7 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid <= 0) return 0;
-  gemm_kernel<BN, MODE, BMN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH((gemm_kernel<BN, MODE, BMN>), grid, kGemmThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmC, tmC2, p);
   return 0;
 }
 
@@ -488,6 +493,10 @@ void passt_gemm_debug_desc(int active, const unsigned* v6) {
 
 // 1 (default): use the 2-CTA (cta_group::2) kernel where the shape allows; 0: always the 1-CTA kernel.
 void passt_gemm_set_2cta(int enable) { pb::g_use_2cta = enable; }
+
+// 1 (default): launch the hot-path kernels with programmatic dependent launch (common.cuh pdl_gate); 0: plain launches.
+void passt_set_pdl(int enable) { pb::g_pdl_enabled = enable ? 1 : 0; }
+int passt_get_pdl(void) { return pb::g_pdl_enabled; }
 
 int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                     int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,

@@ -125,7 +125,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    if (MODE == kBiasGeluBf16 || MODE == kGeluGradBf16) tma_prefetch_desc(&tmC2);
+    if (MODE == kBiasGeluBf16 || MODE == kGeluGradBf16 || MODE == kRowDotBf16) tma_prefetch_desc(&tmC2);
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -134,7 +134,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * kEpiWarps);
     }
-    if (MODE == kGeluGradBf16)
+    if (MODE == kGeluGradBf16 || MODE == kRowDotBf16)
       for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
@@ -143,6 +143,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();   // everything above is on-chip; global memory is first touched below
 
   // work items are 256x256 cluster tiles
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;    // m_tiles counts 256-row blocks here
@@ -247,7 +248,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // mode 3: the gelu' operand (tmC2 is its tensor map) does not depend on the accumulator.  Each warp pulls its
       // 32x32 blocks with TMA into its own two staging buffers *before* waiting for the tile, reads them back
       // row-per-lane (same 64 B swizzle as the output), and then reuses the buffer for the output block.
-      if (MODE == kGeluGradBf16) {
+      if (MODE == kGeluGradBf16 || MODE == kRowDotBf16) {
         if (lane == 0) {
           tma_store_wait_read<0>();          // both staging buffers have been read by the previous tile's stores
 #pragma unroll
@@ -298,7 +299,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
-          if (MODE == kGeluGradBf16) {
+          if (MODE == kGeluGradBf16 || MODE == kRowDotBf16) {
             const int ab = ci & 1;               // chunks 0 and 2 use buffer 0, chunk 1 buffer 1
             if (ci == 1 && slot + 2 * kEpiSlots < BN / Cfg::kColsPerChunk) {
               // third block of this tile: its aux goes into buffer 0 as soon as block 0's store has read it
@@ -315,6 +316,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             buf = ab;                            // the output block goes back into the buffer the aux came in
             const uint8_t* abuf = my_epi + ab * Cfg::kEpiBufBytes;
             // rows >= M arrive as zeros (TMA zero-fills out-of-bounds rows; their accumulator rows are zero as well)
+            float dot = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 u = *reinterpret_cast<const uint4*>(abuf + lane * 64 + ((uint32_t(i) ^ swz) << 4));
@@ -322,11 +324,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 // bf16 -> fp32 is a 16-bit shift
-                v[i * 8 + 2 * j] *= __uint_as_float(w[j] << 16);
-                v[i * 8 + 2 * j + 1] *= __uint_as_float(w[j] & 0xffff0000u);
+                if (MODE == kGeluGradBf16) {
+                  v[i * 8 + 2 * j] *= __uint_as_float(w[j] << 16);
+                  v[i * 8 + 2 * j + 1] *= __uint_as_float(w[j] & 0xffff0000u);
+                } else {
+                  // D = rowsum(dO o O) over the bf16-rounded dO the attention backward will read
+                  const float d0 = __bfloat162float(__float2bfloat16(v[i * 8 + 2 * j]));
+                  const float d1 = __bfloat162float(__float2bfloat16(v[i * 8 + 2 * j + 1]));
+                  dot = fmaf(d0, __uint_as_float(w[j] << 16), dot);
+                  dot = fmaf(d1, __uint_as_float(w[j] & 0xffff0000u), dot);
+                }
               }
             }
-            if (p.bias != nullptr) {
+            if (MODE == kRowDotBf16) {
+              // this 32-column block is half of head (col0 / 64): two atomics per (token, head) in total
+              if (row < p.M) {
+                const int clip = row / p.aux_period, tok = row - clip * p.aux_period;
+                const int npad = ((p.aux_period + 127) >> 7) << 7;
+                atomicAdd(const_cast<float*>(p.bias) + (size_t(clip) * (p.N >> 6) + (col0 >> 6)) * npad + tok, dot);
+              }
+            }
+            if (MODE == kGeluGradBf16 && p.bias != nullptr) {
               // bias gradient of the layer that produced `pre`: column sums of this 32x32 block (rows >= M are 0).
               // One plain store per (quadrant, column): every such slot is written exactly once per tile.
               float cs[32];
@@ -346,7 +364,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               w2[i] = g.x; w2[i + 1] = g.y;
             }
           }
-          if (MODE != kGeluGradBf16) {
+          if (MODE != kGeluGradBf16 && MODE != kRowDotBf16) {
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
           }
@@ -403,6 +421,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 4; ++i) {
                 const float4 t4 = __ldg(tp + i);
                 v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+              }
+              if (p.bias != nullptr) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 b4 = __ldg(bp + i);
+                  v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                }
               }
             }
           }
@@ -491,8 +517,9 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
       if ((rc = make_tmap_2d(&tmC2, C2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ldc) * 2, 32, 32,
                              CU_TENSOR_MAP_SWIZZLE_64B)))
         return rc;
-    } else if (MODE == kGeluGradBf16) {
+    } else if (MODE == kGeluGradBf16 || MODE == kRowDotBf16) {
       if (aux == nullptr || (ld_aux % 8)) return PB_ERR_BAD_ARG;
+      if (MODE == kRowDotBf16 && (bias == nullptr || aux_period <= 0 || (N % 64) != 0)) return PB_ERR_BAD_ARG;
       if ((rc = make_tmap_2d(&tmC2, aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, uint64_t(ld_aux) * 2, 32, 32,
                              CU_TENSOR_MAP_SWIZZLE_64B)))
         return rc;
@@ -524,8 +551,7 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
   if (clusters <= 0) return 0;
-  gemm2_kernel<MODE, BMN><<<clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH((gemm2_kernel<MODE, BMN>), clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmC, tmC2, p);
   return 0;
 }
 
@@ -541,6 +567,7 @@ int launch_gemm2(int mode, const void* A, const void* B, void* C, void* C2, cons
     case kWgradF32: return PB_G2(kWgradF32, false);
     case kBiasBf16 | kBRowMajorKN: return PB_G2(kBiasBf16, true);
     case kGeluGradBf16 | kBRowMajorKN: return PB_G2(kGeluGradBf16, true);
+    case kRowDotBf16 | kBRowMajorKN: return PB_G2(kRowDotBf16, true);
     default: return PB_ERR_BAD_ARG;
   }
 #undef PB_G2

@@ -7,9 +7,11 @@ namespace pb {
 enum GemmMode : int {
   kBiasBf16 = 0,      // C = bf16(acc + bias)
   kBiasGeluBf16 = 1,  // C = bf16(gelu'(acc + bias)), C2 = bf16(gelu(acc + bias))
-  kRowTabF32 = 2,     // C = fp32(acc + tab[row % period, col])
+  kRowTabF32 = 2,     // C = fp32(acc + tab[row % period, col] (+ bias[col]))  -- period >= M: a full residual tensor
   kGeluGradBf16 = 3,  // C = bf16(acc * aux[row, col])   (aux = gelu'(pre) saved by mode 1)
   kWgradF32 = 4,      // C += fp32(acc)   (MN-major operands, split-K, TMA reduce-add)
+  kRowDotBf16 = 5,    // C = bf16(acc);  dsum[(row / period) , col / 64, row % period] += sum_{64-col group} C * aux
+                      //   (attention backward's D = rowsum(dO o O) folded into the proj-dgrad GEMM; needs kBRowMajorKN)
   kBRowMajorKN = 16,  // flag for modes 0 / 3: B is given as [K, N] row-major (the nn.Linear weight itself for dgrad)
 };
 
@@ -26,8 +28,9 @@ struct GemmParams {
   int k_blocks;            // total BK blocks along K
   int splits;              // split-K factor (1 for TN modes)
   const float* bias;       // [N] or nullptr.  mode 3: OUTPUT (float*), += column sums of C (bias gradient) if non-null
-  const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 gelu'(pre) [M, ld_aux]
-  int aux_period;          // mode 2
+                           // mode 5: OUTPUT (float*) dsum [M / period, N / 64, npad] (npad = 128 * ceil(period / 128))
+  const void* aux;         // mode 2: float tab[period, N]; mode 3: bf16 gelu'(pre) [M, ld_aux]; mode 5: bf16 O [M, ld_aux]
+  int aux_period;          // mode 2: table rows; mode 5: tokens per clip
   int ld_aux;              // elements
   // UMMA smem-descriptor strides; exposed so the bring-up test can probe alternatives without a rebuild
   uint32_t lbo_a, sbo_a, kstep_a;  // bytes

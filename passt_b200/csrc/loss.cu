@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256)
 loss_bce_kernel(const float* __restrict__ logits, const float* __restrict__ target, const int* __restrict__ perm,
                 const float* __restrict__ lam, float* __restrict__ loss, float* __restrict__ dlogits,
                 float* partial, unsigned* ticket, int B, int C) {
+  pdl_gate();
   __shared__ float scratch[8];
   const int b = blockIdx.x;
   const float inv_count = 1.0f / (float(B) * float(C));
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256)
 loss_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target, const int* __restrict__ perm,
                const float* __restrict__ lam, float* __restrict__ loss, float* __restrict__ dlogits, float* partial,
                unsigned* ticket, int B, int C) {
+  pdl_gate();
   __shared__ float scratch[8];
   const int b = blockIdx.x;
   const float* z = logits + size_t(b) * C;
@@ -118,6 +120,7 @@ loss_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ t
 
 __global__ void __launch_bounds__(256)
 scale_dev_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ s, size_t n) {
+  pdl_gate();
   const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
   if (i < n) out[i] = in[i] * s[0];
 }
@@ -222,9 +225,8 @@ int passt_loss_bce(const float* logits, const float* target, const int* perm, co
   using namespace pb;
   if (!logits || !target || !loss || !workspace || B <= 0 || C <= 0) return PB_ERR_BAD_ARG;
   if ((perm == nullptr) != (lam == nullptr)) return PB_ERR_BAD_ARG;
-  loss_bce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, target, perm, lam, loss, dlogits,
-                                                       reinterpret_cast<float*>(workspace), ticket_of(workspace, B), B, C);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(loss_bce_kernel, B, 256, 0, (cudaStream_t)stream, logits, target, perm, lam, loss, dlogits,
+            reinterpret_cast<float*>(workspace), ticket_of(workspace, B), B, C);
   return 0;
 }
 
@@ -233,9 +235,8 @@ int passt_loss_ce(const float* logits, const long long* target, const int* perm,
   using namespace pb;
   if (!logits || !target || !loss || !workspace || B <= 0 || C <= 0) return PB_ERR_BAD_ARG;
   if ((perm == nullptr) != (lam == nullptr)) return PB_ERR_BAD_ARG;
-  loss_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, target, perm, lam, loss, dlogits,
-                                                      reinterpret_cast<float*>(workspace), ticket_of(workspace, B), B, C);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(loss_ce_kernel, B, 256, 0, (cudaStream_t)stream, logits, target, perm, lam, loss, dlogits,
+            reinterpret_cast<float*>(workspace), ticket_of(workspace, B), B, C);
   return 0;
 }
 
@@ -243,8 +244,7 @@ int passt_scale_dev(float* out, const float* in, const float* scalar_dev, size_t
   using namespace pb;
   if (!out || !in || !scalar_dev) return PB_ERR_BAD_ARG;
   if (n == 0) return 0;
-  scale_dev_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, in, scalar_dev, n);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(scale_dev_kernel, unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream, out, in, scalar_dev, n);
   return 0;
 }
 

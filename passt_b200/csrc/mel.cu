@@ -61,6 +61,7 @@ __global__ void mel_tables_kernel(MelTables* t, int win_length) {
 // mel endpoints come in as doubles computed the way the python scalars are (mel_scale_scalar uses math.log).
 __global__ void mel_bank_kernel(MelBank* bank, double mel_low, double mel_high, float sample_rate,
                                 const double* __restrict__ band_dev) {
+  pdl_gate();
   __shared__ float melk[kHalf];
   const int tid = threadIdx.x;
   if (band_dev != nullptr) {   // (fmin, fmax) live in device memory (CUDA-graph replays with per-step augmentation)
@@ -195,6 +196,7 @@ struct MelSmem {
 
 __global__ void __launch_bounds__(kMelWarps * 32, 2)
 mel_kernel(const MelParams p, const MelTables* __restrict__ tabs, const MelBank* __restrict__ bank) {
+  pdl_gate();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float2* s_tw = reinterpret_cast<float2*>(smem_raw + MelSmem::kTw);
   float2* s_t2 = reinterpret_cast<float2*>(smem_raw + MelSmem::kT2);
@@ -359,9 +361,8 @@ int passt_mel_set_band(void* workspace, double fmin, double fmax, int sample_rat
                                              ((sizeof(MelTables) + 255) / 256) * 256);
   const double mel_low = 1127.0 * log(1.0 + fmin / 700.0);
   const double mel_high = 1127.0 * log(1.0 + fmax / 700.0);
-  mel_bank_kernel<<<1, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(bank, mel_low, mel_high,
-                                                                         float(sample_rate), nullptr);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(mel_bank_kernel, 1, 512, 0, reinterpret_cast<cudaStream_t>(stream), bank, mel_low, mel_high,
+            float(sample_rate), (const double*)nullptr);
   return 0;
 }
 
@@ -372,8 +373,8 @@ int passt_mel_set_band_dev(void* workspace, const double* band_dev, int sample_r
   if (!workspace || !band_dev) return PB_ERR_BAD_ARG;
   MelBank* bank = reinterpret_cast<MelBank*>(reinterpret_cast<uint8_t*>(workspace) +
                                              ((sizeof(MelTables) + 255) / 256) * 256);
-  mel_bank_kernel<<<1, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(bank, 0.0, 0.0, float(sample_rate), band_dev);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(mel_bank_kernel, 1, 512, 0, reinterpret_cast<cudaStream_t>(stream), bank, 0.0, 0.0, float(sample_rate),
+            band_dev);
   return 0;
 }
 
@@ -391,8 +392,7 @@ int passt_mel_forward(const void* workspace, const float* wave, float* out, int 
   p.rnd = rnd; p.freqm = freqm; p.timem = timem; p.preemph = 0.97f;
   PB_SET_SMEM_ONCE(kMelSmemBytes, mel_kernel);
   dim3 grid((p.T + kFramesPerCta - 1) / kFramesPerCta, B);
-  mel_kernel<<<grid, kMelWarps * 32, kMelSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(p, t, bank);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(mel_kernel, grid, kMelWarps * 32, kMelSmemBytes, reinterpret_cast<cudaStream_t>(stream), p, t, bank);
   return 0;
 }
 

@@ -29,6 +29,7 @@ constexpr int kAdamElemsPerBlock = 4096;   // 256 threads x 4 groups x 4 element
 // hyper: [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] step (float, advanced here)
 //        [6] lr / (1 - beta1^t)   [7] 1 / sqrt(1 - beta2^t)        (outputs of this kernel)
 __global__ void adamw_prepare_kernel(float* __restrict__ hyper) {
+  pdl_gate();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float t = hyper[5] + 1.0f;
   hyper[5] = t;
@@ -49,6 +50,7 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamEntry* __restrict__ table, int n_entries, const float* __restrict__ hyper) {
+  pdl_gate();
   __shared__ int s_e;
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_entries - 1;
@@ -180,10 +182,9 @@ int passt_adamw_step(const void* table, int n_entries, int total_blocks, float* 
   using namespace pb;
   if (table == nullptr || hyper == nullptr || n_entries <= 0 || total_blocks <= 0) return PB_ERR_BAD_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adamw_prepare_kernel<<<1, 32, 0, st>>>(hyper);
-  PB_LAUNCH_CHECK();
-  adamw_multi_kernel<<<total_blocks, 256, 0, st>>>(reinterpret_cast<const AdamEntry*>(table), n_entries, hyper);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(adamw_prepare_kernel, 1, 32, 0, st, hyper);
+  PB_LAUNCH(adamw_multi_kernel, total_blocks, 256, 0, st, reinterpret_cast<const AdamEntry*>(table), n_entries,
+            (const float*)hyper);
   return 0;
 }
 

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ delta, float* __restrict__ x_out,
               __nv_bfloat16* __restrict__ h, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               const float* __restrict__ gamma, const float* __restrict__ beta, int M, float eps) {
+  pdl_gate();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -86,6 +87,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* g_in,
               float* g_out, __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ colsum, int M, int rows_per_cta) {
+  pdl_gate();
   extern __shared__ float4 ln_acc4[];
   float* acc_all = reinterpret_cast<float*>(ln_acc4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ mel, void* __restrict__ A, const int* __restrict__ patch_f,
               const int* __restrict__ patch_t, int B, int ntok, int Fm, int Tm, int fstride, int tstride,
               const int* __restrict__ mix_perm, const float* __restrict__ mix_lam) {
+  pdl_gate();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= B * ntok) return;
@@ -252,6 +255,7 @@ __global__ void token_table_kernel(float* __restrict__ tab, const float* __restr
                                    const float* __restrict__ freq_pos, const int* __restrict__ patch_f,
                                    const int* __restrict__ patch_t, int ntok, int Fg, int Tg, int toff,
                                    const int* __restrict__ toff_dev) {
+  pdl_gate();
   const int n = blockIdx.x;
   if (toff_dev != nullptr) toff = *toff_dev;   // device-resident offset (CUDA-graph replays)
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
@@ -269,6 +273,7 @@ token_table_bwd_kernel(const float* __restrict__ g0, float* __restrict__ dcls, f
                        float* __restrict__ dnew_pos, float* __restrict__ dconv_bias, float* __restrict__ dtime,
                        float* __restrict__ dfreq, const int* __restrict__ patch_f, const int* __restrict__ patch_t,
                        int B, int ntok, int Fg, int Tg, int toff, const int* __restrict__ toff_dev) {
+  pdl_gate();
   const int n = blockIdx.x;
   if (toff_dev != nullptr) toff = *toff_dev;
   const int c = threadIdx.x * 4;
@@ -345,6 +350,7 @@ struct CastEntry {
 constexpr int kCastGroupsPerBlock = 1024;   // 256 threads x 4 groups of 8 elements
 __global__ void __launch_bounds__(256)
 cast_multi_kernel(const CastEntry* __restrict__ table, int n_entries) {
+  pdl_gate();
   __shared__ int s_e;
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_entries - 1;
@@ -406,6 +412,7 @@ struct HeadParams {
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const HeadParams p, float* __restrict__ logits, float* __restrict__ features,
                 float* __restrict__ fl_out) {
+  pdl_gate();
   __shared__ float scratch[8];
   __shared__ float s_fl[D];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -479,6 +486,7 @@ head_bwd_kernel(const HeadParams p, const float* __restrict__ dlogits, const flo
                 float* __restrict__ g_out, __nv_bfloat16* __restrict__ g_out_bf16, float* __restrict__ d_norm_g,
                 float* __restrict__ d_norm_b, float* __restrict__ d_hln_g, float* __restrict__ d_hln_b,
                 float* __restrict__ colsum) {
+  pdl_gate();
   __shared__ float scratch[8];
   __shared__ float s_dl[1024];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -586,6 +594,7 @@ head_bwd_kernel(const HeadParams p, const float* __restrict__ dlogits, const flo
 __global__ void __launch_bounds__(256)
 head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ fl, float* __restrict__ dW,
                   float* __restrict__ db, int B, int C) {
+  pdl_gate();
   const int cls = blockIdx.x, tid = threadIdx.x;
   float acc[3] = {0.f, 0.f, 0.f};
   float sb = 0.f;
@@ -612,9 +621,8 @@ int passt_ln_fwd(const float* x_in, const void* delta_bf16, float* x_out, void* 
   using namespace pb;
   if (dim != D || M <= 0) return PB_ERR_BAD_ARG;
   const int threads = 256, rows_per_cta = threads / 32;
-  ln_fwd_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, threads, 0, (cudaStream_t)stream>>>(
-      x_in, (const __nv_bfloat16*)delta_bf16, x_out, (__nv_bfloat16*)h_bf16, mean, rstd, gamma, beta, M, eps);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(ln_fwd_kernel, (M + rows_per_cta - 1) / rows_per_cta, threads, 0, (cudaStream_t)stream, x_in,
+            (const __nv_bfloat16*)delta_bf16, x_out, (__nv_bfloat16*)h_bf16, mean, rstd, gamma, beta, M, eps);
   return 0;
 }
 
@@ -628,10 +636,8 @@ int passt_ln_bwd(const void* dh_bf16, const float* x, const float* mean, const f
   if (rows_per_cta < kLnBwdWarps) rows_per_cta = kLnBwdWarps;
   ctas = (M + rows_per_cta - 1) / rows_per_cta;
   PB_SET_SMEM_ONCE(kLnBwdSmem, ln_bwd_kernel);
-  ln_bwd_kernel<<<ctas, kLnBwdWarps * 32, kLnBwdSmem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dh_bf16, x, mean, rstd, gamma, g_in, g_out, (__nv_bfloat16*)g_out_bf16, dgamma, dbeta,
-      colsum, M, rows_per_cta);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(ln_bwd_kernel, ctas, kLnBwdWarps * 32, kLnBwdSmem, (cudaStream_t)stream, (const __nv_bfloat16*)dh_bf16, x,
+            mean, rstd, gamma, g_in, g_out, (__nv_bfloat16*)g_out_bf16, dgamma, dbeta, colsum, M, rows_per_cta);
   return 0;
 }
 
@@ -655,9 +661,8 @@ int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* 
   if (B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
   const long long warps = (long long)B * ntok;
   const int blocks = int((warps * 32 + 255) / 256);
-  im2col_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, A_bf16, patch_f, patch_t, B, ntok, Fm, Tm,
-                                                                 fstride, tstride, mix_perm, mix_lam);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(im2col_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, mel, A_bf16, patch_f, patch_t, B, ntok, Fm, Tm,
+            fstride, tstride, mix_perm, mix_lam);
   return 0;
 }
 
@@ -679,9 +684,8 @@ int passt_token_table(float* tab, const float* cls, const float* dist, const flo
                       const int* patch_t, int ntok, int Fg, int Tg, int toff, const int* toff_dev, void* stream) {
   using namespace pb;
   if (ntok < 2) return PB_ERR_BAD_ARG;
-  token_table_kernel<<<ntok, 256, 0, (cudaStream_t)stream>>>(tab, cls, dist, new_pos, conv_bias, time_pos, freq_pos,
-                                                             patch_f, patch_t, ntok, Fg, Tg, toff, toff_dev);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(token_table_kernel, ntok, 256, 0, (cudaStream_t)stream, tab, cls, dist, new_pos, conv_bias, time_pos,
+            freq_pos, patch_f, patch_t, ntok, Fg, Tg, toff, toff_dev);
   return 0;
 }
 
@@ -690,9 +694,8 @@ int passt_token_table_bwd(const float* g0, float* dcls, float* ddist, float* dne
                           int Fg, int Tg, int toff, const int* toff_dev, void* stream) {
   using namespace pb;
   if (ntok < 2 || B <= 0) return PB_ERR_BAD_ARG;
-  token_table_bwd_kernel<<<ntok, 192, 0, (cudaStream_t)stream>>>(g0, dcls, ddist, dnew_pos, dconv_bias, dtime, dfreq,
-                                                                 patch_f, patch_t, B, ntok, Fg, Tg, toff, toff_dev);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(token_table_bwd_kernel, ntok, 192, 0, (cudaStream_t)stream, g0, dcls, ddist, dnew_pos, dconv_bias, dtime,
+            dfreq, patch_f, patch_t, B, ntok, Fg, Tg, toff, toff_dev);
   return 0;
 }
 
@@ -717,9 +720,8 @@ int passt_cast_multi(const void* table, int n_entries, int total_blocks, void* s
   using namespace pb;
   static_assert(sizeof(CastEntry) == 32, "CastEntry layout is part of the C ABI");
   if (table == nullptr || n_entries <= 0 || total_blocks <= 0) return PB_ERR_BAD_ARG;
-  cast_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const CastEntry*>(table),
-                                                                    n_entries);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(cast_multi_kernel, total_blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const CastEntry*>(table),
+            n_entries);
   return 0;
 }
 
@@ -729,8 +731,7 @@ int passt_head_fwd(const float* x, const void* delta_bf16, const float* norm_g, 
   using namespace pb;
   if (B <= 0 || C <= 0 || C > 1024) return PB_ERR_BAD_ARG;
   HeadParams p{x, (const __nv_bfloat16*)delta_bf16, norm_g, norm_b, hln_g, hln_b, W, bias, B, ntok, C, 1e-6f, 1e-5f};
-  head_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p, logits, features, fl);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(head_fwd_kernel, B, 256, 0, (cudaStream_t)stream, p, logits, features, fl);
   return 0;
 }
 
@@ -742,12 +743,10 @@ int passt_head_bwd(const float* x, const void* delta_bf16, const float* norm_g, 
   using namespace pb;
   if (B <= 0 || C <= 0 || C > 1024) return PB_ERR_BAD_ARG;
   HeadParams p{x, (const __nv_bfloat16*)delta_bf16, norm_g, norm_b, hln_g, hln_b, W, nullptr, B, ntok, C, 1e-6f, 1e-5f};
-  head_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(p, dlogits, dfeatures, g_out, (__nv_bfloat16*)g_out_bf16,
-                                                       d_norm_g, d_norm_b, d_hln_g, d_hln_b, colsum);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH(head_bwd_kernel, B, 256, 0, (cudaStream_t)stream, p, dlogits, dfeatures, g_out, (__nv_bfloat16*)g_out_bf16,
+            d_norm_g, d_norm_b, d_hln_g, d_hln_b, colsum);
   if (dlogits) {
-    head_wgrad_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dlogits, fl, dW, dbias, B, C);
-    PB_LAUNCH_CHECK();
+    PB_LAUNCH(head_wgrad_kernel, C, 256, 0, (cudaStream_t)stream, dlogits, fl, dW, dbias, B, C);
   }
   return 0;
 }

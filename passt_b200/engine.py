@@ -182,6 +182,13 @@ class WeightCache:
 
 
 B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMajorKN)
+# A/B switches (environment, read once): both default on
+#   PASST_B200_FUSE_RESID : residual adds (x + proj(att), x + fc2(act)) run in the proj / fc2 GEMM epilogues (fp32 output
+#                           = acc + bias + residual); the LayerNorm pass then only reads the fp32 stream
+#   PASST_B200_FUSE_DSUM  : attention backward's D = rowsum(dO o O) is accumulated by the proj-dgrad GEMM epilogue
+import os as _os
+FUSE_RESID = _os.environ.get("PASST_B200_FUSE_RESID", "1") != "0"
+FUSE_DSUM = _os.environ.get("PASST_B200_FUSE_DSUM", "1") != "0"
 GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
 
 
@@ -392,6 +399,7 @@ class PasstFunction(torch.autograd.Function):
         saved = []
         delta = None
         scale = float((Dm // H) ** -0.5)
+        fuse = FUSE_RESID
         for i in range(depth):
             pre = f"blocks.{i}."
             wqkv, _ = wc.get(P[pre + "attn.qkv.weight"], False)
@@ -414,24 +422,39 @@ class PasstFunction(torch.autograd.Function):
             att = torch.empty(M, Dm, **b16)
             lse = torch.empty(B, H, ((ntok + 127) // 128) * 128, **f32)   # log2-domain, padded to whole query tiles
             L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(att), L.ptr(lse), B, ntok, H, scale, st)
-            oproj = torch.empty(M, Dm, **b16)
-            _gemm(att, wproj, oproj, bias=P[pre + "attn.proj.bias"], M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)
             x_mid = torch.empty(M, Dm, **f32)
             h2 = torch.empty(M, Dm, **b16)
             mean2 = torch.empty(M, **f32); rstd2 = torch.empty(M, **f32)
-            L.call("passt_ln_fwd", L.ptr(x_in), L.ptr(oproj), L.ptr(x_mid), L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
-                   L.ptr(P[pre + "norm2.weight"]), L.ptr(P[pre + "norm2.bias"]), M, Dm, 1e-6, st)
+            if fuse:
+                # x_mid = x_in + att Wproj^T + bias straight from the GEMM epilogue (fp32), then LN reads it once
+                _gemm(att, wproj, x_mid, bias=P[pre + "attn.proj.bias"], aux=x_in, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm,
+                      ldc=Dm, mode=2, period=M, ld_aux=Dm)
+                L.call("passt_ln_fwd", L.ptr(x_mid), None, None, L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
+                       L.ptr(P[pre + "norm2.weight"]), L.ptr(P[pre + "norm2.bias"]), M, Dm, 1e-6, st)
+            else:
+                oproj = torch.empty(M, Dm, **b16)
+                _gemm(att, wproj, oproj, bias=P[pre + "attn.proj.bias"], M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0)
+                L.call("passt_ln_fwd", L.ptr(x_in), L.ptr(oproj), L.ptr(x_mid), L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
+                       L.ptr(P[pre + "norm2.weight"]), L.ptr(P[pre + "norm2.bias"]), M, Dm, 1e-6, st)
             pre_act = torch.empty(M, hidden, **b16)
             act = torch.empty(M, hidden, **b16)
             _gemm(h2, wfc1, pre_act, C2=act, bias=P[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm, ldb=Dm,
                   ldc=hidden, mode=1)
-            ofc2 = torch.empty(M, Dm, **b16)
-            _gemm(act, wfc2, ofc2, bias=P[pre + "mlp.fc2.bias"], M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden, ldc=Dm,
-                  mode=0)
+            if fuse:
+                x_next = torch.empty(M, Dm, **f32)
+                _gemm(act, wfc2, x_next, bias=P[pre + "mlp.fc2.bias"], aux=x_mid, M=M, N=Dm, K=hidden, lda=hidden,
+                      ldb=hidden, ldc=Dm, mode=2, period=M, ld_aux=Dm)
+            else:
+                ofc2 = torch.empty(M, Dm, **b16)
+                _gemm(act, wfc2, ofc2, bias=P[pre + "mlp.fc2.bias"], M=M, N=Dm, K=hidden, lda=hidden, ldb=hidden,
+                      ldc=Dm, mode=0)
             if need_grad:
                 saved.append(dict(x_in=x_in, mean1=mean1, rstd1=rstd1, h1=h1, qkv=qkv, att=att, lse=lse, x_mid=x_mid,
                                   mean2=mean2, rstd2=rstd2, h2=h2, pre_act=pre_act, act=act))
-            xcur, delta = x_mid, ofc2
+            if fuse:
+                xcur, delta = x_next, None
+            else:
+                xcur, delta = x_mid, ofc2
 
         C = P["head.1.weight"].shape[0]
         logits = torch.empty(B, C, **f32)
@@ -494,6 +517,7 @@ class PasstFunction(torch.autograd.Function):
 
         ws_bytes = L.load().passt_attn_bwd_workspace_bytes(B, ntok, H)
         attn_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dsum_ptr = L.load().passt_attn_bwd_dsum_ptr(L.ptr(attn_ws), B, ntok, H) if FUSE_DSUM else None
         dact = torch.empty(M, hidden, **b16)
         dh = torch.empty(M, Dm, **b16)
         datt = torch.empty(M, Dm, **b16)
@@ -518,11 +542,18 @@ class PasstFunction(torch.autograd.Function):
                    L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm2.weight"]),
                    L.ptr(G[pre + "norm2.bias"]), L.ptr(G[pre + "attn.proj.bias"]), M, Dm, st)
             # ---- attention
-            _gemm(gb, wproj, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
+            if FUSE_DSUM:
+                # d att = g Wproj with D = rowsum(d att o att) accumulated by the same epilogue (workspace zeroed first)
+                L.call("passt_attn_bwd_prepare", L.ptr(attn_ws), B, ntok, H, st)
+                _gemm(gb, wproj, datt, bias=dsum_ptr, aux=S["att"], M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm,
+                      mode=5 | B_KN, period=ntok, ld_aux=Dm)
+            else:
+                _gemm(gb, wproj, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(gb, S["att"], G[pre + "attn.proj.weight"], M=Dm, N=Dm, K=M, lda=Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(Dm, Dm, M))
-            L.call("passt_attn_bwd", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
-                   L.ptr(G[pre + "attn.qkv.bias"]), L.ptr(attn_ws), B, ntok, H, scale, st)   # + qkv bias gradient
+            L.call("passt_attn_bwd_ex", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
+                   L.ptr(G[pre + "attn.qkv.bias"]), L.ptr(attn_ws), B, ntok, H, scale, 1 if FUSE_DSUM else 0,
+                   st)   # + qkv bias gradient
             _gemm(dqkv, wqkv, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(dqkv, S["h1"], G[pre + "attn.qkv.weight"], M=3 * Dm, N=Dm, K=M, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=4,
                   splits=_wgrad_splits(3 * Dm, Dm, M))

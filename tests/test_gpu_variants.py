@@ -1,0 +1,124 @@
+"""A/B switches of the kernel path: every variant must give the same results (through the C ABI).
+
+  * attention forward: ping-pong kernel (attn_fwd2.cu, default) vs the two-CTAs-per-SM kernel (attn_fwd.cu) vs a torch
+    fp32 softmax-attention reference, for token counts with even / odd / single query-tile counts;
+  * programmatic dependent launch on / off;
+  * residual adds fused into the proj / fc2 GEMM epilogues on / off;
+  * attention-backward D = rowsum(dO o O) fused into the proj-dgrad GEMM epilogue on / off.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import grad_metrics, quiet, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _attn_ref(qkv, H):
+    B, N, C3 = qkv.shape
+    C = C3 // 3
+    q, k, v = qkv.float().reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+    att = ((q @ k.transpose(-2, -1)) * (C // H) ** -0.5).softmax(-1)
+    return (att @ v).transpose(1, 2).reshape(B, N, C), torch.logsumexp((q @ k.transpose(-2, -1)) * (C // H) ** -0.5, -1)
+
+
+@pytest.mark.parametrize("N", [474, 353, 790, 130, 1190, 64])
+def test_attention_forward_variants_agree(N):
+    from passt_b200 import _lib as L
+    B, H = 3, 12
+    C = H * 64
+    torch.manual_seed(N)
+    qkv = (torch.randn(B, N, 3 * C, device=DEV) * 1.5).bfloat16()
+    npad = ((N + 127) // 128) * 128
+    outs = {}
+    for variant in (1, 2):
+        L.load().passt_attn_fwd_set_variant(variant)
+        o = torch.zeros(B, N, C, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, npad, device=DEV)
+        L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(o), L.ptr(lse), B, N, H, 0.125, L.stream_ptr())
+        torch.cuda.synchronize()
+        outs[variant] = (o, lse)
+    L.load().passt_attn_fwd_set_variant(2)
+    ref_o, ref_lse = _attn_ref(qkv, H)
+    for variant in (1, 2):
+        o, lse = outs[variant]
+        assert relerr(o, ref_o) < 1e-2, variant
+        # log2-domain LSE of the scaled scores; pad rows are +inf
+        got = lse[:, :, :N] * 0.6931471805599453
+        assert (got - ref_lse).abs().max().item() < 2e-3, variant
+        assert torch.isinf(lse[:, :, N:]).all()
+    assert relerr(outs[2][0], outs[1][0]) < 4e-3          # same per-row arithmetic; bf16 output rounding at most
+
+
+def _small_train_net(seed=0):
+    from passt_b200.passt import get_model, lighten_model
+    torch.manual_seed(seed)
+    with quiet():
+        net = lighten_model(get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, s_patchout_t=40,
+                                      s_patchout_f=4), cut_depth=9)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.01 * torch.randn(p.shape, generator=g))
+    return net.to(DEV).train()
+
+
+def _run(net, x, y):
+    net.zero_grad(set_to_none=True)
+    torch.manual_seed(9)
+    logits, _ = net(x)
+    F.binary_cross_entropy_with_logits(logits, y).backward()
+    torch.cuda.synchronize()
+    return logits.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+
+def test_pdl_on_off_same_results():
+    from passt_b200 import _lib as L
+    net = _small_train_net()
+    torch.manual_seed(3)
+    x = torch.randn(4, 1, 128, 1000, device=DEV)
+    y = (torch.rand(4, 527, device=DEV) < 0.05).float()
+    lib = L.load()
+    was = lib.passt_get_pdl()
+    try:
+        lib.passt_set_pdl(1)
+        la, ga = _run(net, x, y)
+        la2, ga2 = _run(net, x, y)
+        lib.passt_set_pdl(0)
+        lb, gb = _run(net, x, y)
+    finally:
+        lib.passt_set_pdl(was)
+    assert torch.equal(la, lb) and torch.equal(la, la2)
+    for k in ga:
+        # gradients use fp32 atomics / TMA reduce-adds whose order is not fixed: compare against the run-to-run spread
+        assert relerr(gb[k], ga[k]) < 1e-4 + 2 * relerr(ga2[k], ga[k]), k
+
+
+def test_fused_residual_and_dsum_switches():
+    from passt_b200 import engine
+    net = _small_train_net()
+    torch.manual_seed(4)
+    x = torch.randn(4, 1, 128, 1000, device=DEV)
+    y = (torch.rand(4, 527, device=DEV) < 0.05).float()
+    keep = (engine.FUSE_RESID, engine.FUSE_DSUM)
+    try:
+        engine.FUSE_RESID, engine.FUSE_DSUM = False, False
+        l0, g0 = _run(net, x, y)
+        engine.FUSE_RESID, engine.FUSE_DSUM = True, False
+        l1, g1 = _run(net, x, y)
+        engine.FUSE_RESID, engine.FUSE_DSUM = False, True
+        l2, g2 = _run(net, x, y)
+        engine.FUSE_RESID, engine.FUSE_DSUM = True, True
+        l3, g3 = _run(net, x, y)
+    finally:
+        engine.FUSE_RESID, engine.FUSE_DSUM = keep
+    # fused residual: the GEMM output joins the fp32 stream without a bf16 round trip -> tiny, bounded differences
+    assert relerr(l1, l0) < 5e-3 and relerr(l3, l0) < 5e-3
+    assert torch.equal(l2, l0)                                      # D-fusion only touches the backward
+    for k in g0:
+        m = grad_metrics(g2[k], g0[k])
+        assert m["relmax"] < 2e-3 and m["cos"] > 0.99999, (k, m)     # same D up to fp32 summation order
+        m = grad_metrics(g3[k], g0[k])
+        assert m["relmax"] < 1e-2 and m["cos"] > 0.9995, (k, m)
