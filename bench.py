@@ -699,6 +699,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduce runs next to persistent 1-CTA-per-SM kernels: give it a few SMs of its own
+        # (passt_b200.ddp.GradAllReducer(reserve_sms=4)) instead of NCCL's default of up to 32 channels
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

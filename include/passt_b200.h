@@ -73,6 +73,10 @@ void passt_attn_fwd_set_variant(int variant);
 /* programmatic dependent launch of the hot-path kernels (1 = default; environment PASST_B200_PDL=0 turns it off) */
 void passt_set_pdl(int enable);
 int passt_get_pdl(void);
+/* SMs the persistent kernels (GEMMs, attention) occupy, default 148: the data-parallel backward leaves a few SMs to
+ * the NCCL all-reduce kernels that run concurrently (passt_b200/ddp.py) */
+void passt_set_sm_limit(int n_sms);
+int passt_get_sm_limit(void);
 
 /* ---- row kernels ------------------------------------------------------------------------------------------------ */
 /* x_out = x_in (+ delta); h = LayerNorm(x_out) (Block residual + norm1/norm2, models/passt.py:377-380) */

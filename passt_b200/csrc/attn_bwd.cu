@@ -544,7 +544,7 @@ int passt_attn_bwd_ex(const void* qkv, const void* o, const void* dO, const floa
   p.dbias = dbias_qkv;
   p.timeline = pb::g_attn_bwd_timeline;
   PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal, attn_bwd_kernel);
-  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
+  const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
   PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal, st, tmQKV, tmdO, tmdQKV, tmdQacc, p);
   {
     if (C % 256 != 0) return PB_ERR_BAD_ARG;

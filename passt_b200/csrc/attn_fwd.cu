@@ -392,7 +392,7 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   p.total_items = B * H * p.n_qt;
   p.timeline = pb::g_attn_timeline;
   PB_SET_SMEM_ONCE(AttnFwdSmem::kTotal, attn_fwd_kernel);
-  const int grid = p.total_items < 2 * kNumSMs ? p.total_items : 2 * kNumSMs;
+  const int grid = p.total_items < 2 * g_sm_limit ? p.total_items : 2 * g_sm_limit;
   PB_LAUNCH(attn_fwd_kernel, grid, kAttnThreads, AttnFwdSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmO, p);
   return 0;
 }

@@ -375,7 +375,7 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H
   p.n_pairs = (p.n_qt + 1) / 2;
   p.total_items = B * H * p.n_pairs;
   PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal, attn_fwd2_kernel);
-  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
+  const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
   PB_LAUNCH(attn_fwd2_kernel, grid, k2Threads, AttnFwd2Smem::kTotal, st, tmQKV, tmO, p);
   return 0;
 }

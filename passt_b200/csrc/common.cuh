@@ -337,6 +337,9 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
 // host: kernel launch with the PDL attribute (passt_set_pdl(0) turns it off: plain stream-ordered launches)
 // ---------------------------------------------------------------------------------------------
 extern int g_pdl_enabled;
+// SMs the persistent kernels (GEMMs, attention) may occupy: 148 by default; the data-parallel backward lowers it while
+// NCCL all-reduce kernels are in flight so that those get SMs of their own instead of delaying whole GEMM clusters
+extern int g_sm_limit;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                             Args&&... args) {

@@ -399,6 +399,7 @@ int g_pdl_enabled = [] {
   const char* e = getenv("PASST_B200_PDL");      // default on; PASST_B200_PDL=0 or passt_set_pdl(0): plain launches
   return (e != nullptr && e[0] == '0') ? 0 : 1;
 }();
+int g_sm_limit = kNumSMs;
 static int g_use_2cta = 1;   // passt_gemm_set_2cta(): bring-up / A-B switch between the 1-CTA and 2-CTA kernels
 
 template <int BN, int MODE, bool BMN = false>
@@ -473,7 +474,7 @@ static int launch_gemm(const void* A, const void* B, void* C, void* C2, const fl
   }
   PB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm_kernel<BN, MODE, BMN>);
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
-  int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  int grid = num_tiles < g_sm_limit ? num_tiles : g_sm_limit;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid <= 0) return 0;
   PB_LAUNCH((gemm_kernel<BN, MODE, BMN>), grid, kGemmThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmC, tmC2, p);
@@ -497,6 +498,12 @@ void passt_gemm_set_2cta(int enable) { pb::g_use_2cta = enable; }
 // 1 (default): launch the hot-path kernels with programmatic dependent launch (common.cuh pdl_gate); 0: plain launches.
 void passt_set_pdl(int enable) { pb::g_pdl_enabled = enable ? 1 : 0; }
 int passt_get_pdl(void) { return pb::g_pdl_enabled; }
+
+// Number of SMs the persistent kernels may use (clamped to [8, 148]); see g_sm_limit in common.cuh.
+void passt_set_sm_limit(int n_sms) {
+  pb::g_sm_limit = n_sms < 8 ? 8 : (n_sms > pb::kNumSMs ? pb::kNumSMs : n_sms);
+}
+int passt_get_sm_limit(void) { return pb::g_sm_limit; }
 
 int passt_gemm_bf16(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M,
                     int N, int K, int lda, int ldb, int ldc, int mode, int aux_period, int ld_aux, int splits,

@@ -549,7 +549,7 @@ static int launch_gemm2_t(const void* A, const void* B, void* C, void* C2, const
   }
   PB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm2_kernel<MODE, BMN>);
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
-  int clusters = num_tiles < kNumSMs / 2 ? num_tiles : kNumSMs / 2;
+  int clusters = num_tiles < g_sm_limit / 2 ? num_tiles : g_sm_limit / 2;
   if (clusters <= 0) return 0;
   PB_LAUNCH((gemm2_kernel<MODE, BMN>), clusters * 2, kGemmThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmC, tmC2, p);
   return 0;

@@ -25,7 +25,12 @@ import torch.distributed as dist
 
 class GradAllReducer:
     def __init__(self, net: Optional[torch.nn.Module] = None, group=None, average: bool = True,
-                 min_chunk_elems: int = 4 * 1024 * 1024):
+                 min_chunk_elems: int = 4 * 1024 * 1024, reserve_sms: int = 4):
+        """reserve_sms: SMs the backward's persistent kernels (GEMMs, attention) leave free while the chunk all-reduces
+        are in flight (engine.PasstFunction.backward lowers passt_set_sm_limit by this much).  A 148-CTA persistent
+        GEMM cannot share an SM with an NCCL CTA (shared memory), so without the reservation every GEMM that overlaps
+        an all-reduce waits for whole SMs; run NCCL with NCCL_MAX_CTAS <= reserve_sms (bench.py sets it)."""
+        self.reserve_sms = int(reserve_sms)
         self.group = group
         self.average = average
         self.min_chunk = min_chunk_elems

@@ -203,13 +203,13 @@ def _gemm(A, Bm, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, mod
         GEMM_TRACE.append((e0, e1, 2.0 * M * N * K))
 
 
-def _wgrad_splits(M_out: int, N_out: int, tokens: int) -> int:
+def _wgrad_splits(M_out: int, N_out: int, tokens: int, clusters: int = 74) -> int:
     """Split-K factor for the weight-gradient GEMM (2-CTA kernel: 256x256 cluster tiles over 74 clusters).
     Minimises rounds x (k-blocks per split + epilogue cost): enough items to fill the chip in whole waves, few enough
     that the fp32 reduce-add epilogue (one full tile per split) stays amortised."""
     tiles = ((M_out + 255) // 256) * (N_out // 256)
     kb = (tokens + 63) // 64
-    clusters, epi = 74, 8
+    epi = 8
     best, best_cost = 1, None
     for s in range(1, min(kb, 48) + 1):
         per = (kb + s - 1) // s
@@ -496,6 +496,13 @@ class PasstFunction(torch.autograd.Function):
             span[n] = (off, off + s)
             off += s
         hook = getattr(net, "_grad_chunk_hook", None)
+        # data parallel: leave a few SMs to the NCCL all-reduce kernels that run next to the backward's persistent kernels
+        reserve = int(getattr(getattr(hook, "__self__", None), "reserve_sms", 0) or 0) if hook is not None else 0
+        lib = L.load()
+        sm_before = lib.passt_get_sm_limit()
+        if reserve > 0:
+            lib.passt_set_sm_limit(sm_before - reserve)
+        ncl = lib.passt_get_sm_limit() // 2
 
         def chunk_done(first: str, last: str):
             if hook is not None:
@@ -534,10 +541,10 @@ class PasstFunction(torch.autograd.Function):
             _gemm(gb, wfc2, dact, aux=S["pre_act"], bias=G[pre + "mlp.fc1.bias"], M=M, N=hidden, K=Dm, lda=Dm,
                   ldb=hidden, ldc=hidden, mode=3 | B_KN, ld_aux=hidden)   # d pre = (g W2) * gelu'(pre); + fc1 bias grad
             _gemm(gb, S["act"], G[pre + "mlp.fc2.weight"], M=Dm, N=hidden, K=M, lda=Dm, ldb=hidden, ldc=hidden,
-                  mode=4, splits=_wgrad_splits(Dm, hidden, M))
+                  mode=4, splits=_wgrad_splits(Dm, hidden, M, ncl))
             _gemm(dact, wfc1, dh, M=M, N=Dm, K=hidden, lda=hidden, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(dact, S["h2"], G[pre + "mlp.fc1.weight"], M=hidden, N=Dm, K=M, lda=hidden, ldb=Dm, ldc=Dm, mode=4,
-                  splits=_wgrad_splits(hidden, Dm, M))
+                  splits=_wgrad_splits(hidden, Dm, M, ncl))
             L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_mid"]), L.ptr(S["mean2"]), L.ptr(S["rstd2"]),
                    L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm2.weight"]),
                    L.ptr(G[pre + "norm2.bias"]), L.ptr(G[pre + "attn.proj.bias"]), M, Dm, st)
@@ -550,13 +557,13 @@ class PasstFunction(torch.autograd.Function):
             else:
                 _gemm(gb, wproj, datt, M=M, N=Dm, K=Dm, lda=Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(gb, S["att"], G[pre + "attn.proj.weight"], M=Dm, N=Dm, K=M, lda=Dm, ldb=Dm, ldc=Dm, mode=4,
-                  splits=_wgrad_splits(Dm, Dm, M))
+                  splits=_wgrad_splits(Dm, Dm, M, ncl))
             L.call("passt_attn_bwd_ex", L.ptr(S["qkv"]), L.ptr(S["att"]), L.ptr(datt), L.ptr(S["lse"]), L.ptr(dqkv),
                    L.ptr(G[pre + "attn.qkv.bias"]), L.ptr(attn_ws), B, ntok, H, scale, 1 if FUSE_DSUM else 0,
                    st)   # + qkv bias gradient
             _gemm(dqkv, wqkv, dh, M=M, N=Dm, K=3 * Dm, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=0 | B_KN)
             _gemm(dqkv, S["h1"], G[pre + "attn.qkv.weight"], M=3 * Dm, N=Dm, K=M, lda=3 * Dm, ldb=Dm, ldc=Dm, mode=4,
-                  splits=_wgrad_splits(3 * Dm, Dm, M))
+                  splits=_wgrad_splits(3 * Dm, Dm, M, ncl))
             prev_bias = G[f"blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else None
             L.call("passt_ln_bwd", L.ptr(dh), L.ptr(S["x_in"]), L.ptr(S["mean1"]), L.ptr(S["rstd1"]),
                    L.ptr(P[pre + "norm1.weight"]), L.ptr(g), L.ptr(g), L.ptr(gb), L.ptr(G[pre + "norm1.weight"]),
@@ -566,13 +573,14 @@ class PasstFunction(torch.autograd.Function):
             chunk_done(pre + "norm1.weight", pre + "mlp.fc2.bias")
         # ---- patch embedding
         gpe = G["patch_embed.proj.weight"].view(Dm, 256)
-        _gemm(gb, mi["A0"], gpe, M=Dm, N=256, K=M, lda=Dm, ldb=256, ldc=256, mode=4, splits=_wgrad_splits(Dm, 256, M))
+        _gemm(gb, mi["A0"], gpe, M=Dm, N=256, K=M, lda=Dm, ldb=256, ldc=256, mode=4, splits=_wgrad_splits(Dm, 256, M, ncl))
         L.call("passt_token_table_bwd", L.ptr(g), L.ptr(G["cls_token"]), L.ptr(G["dist_token"]),
                L.ptr(G["new_pos_embed"]), L.ptr(G["patch_embed.proj.bias"]), L.ptr(G["time_new_pos_embed"]),
                L.ptr(G["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, Fg, Tg,
                plan.toffset, L.ptr(plan.toffset_dev), st)
         chunk_done("cls_token", "patch_embed.proj.bias")
         net._last_flat_grad = flat
+        lib.passt_set_sm_limit(sm_before)
         ctx.saved = None
         ctx.misc = None
         grads = [G[n] if p.requires_grad else None for n, p in zip(names, params)]
