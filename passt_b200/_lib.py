@@ -30,6 +30,7 @@ _SIGS = {
     "passt_ln_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "passt_colsum_bf16": (i32, [vp, vp, i32, i32, i32, vp]),
     "passt_im2col": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "passt_patch_embed": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "passt_token_table": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "passt_token_table_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "passt_cast_transpose": (i32, [vp, vp, vp, i32, i32, vp]),

@@ -1,0 +1,306 @@
+// passt_b200 — single-kernel patch embedding: TMA gather of the KEPT 16x16 patches -> bf16 operand tile in shared memory
+// -> tcgen05 GEMM against the conv weight -> + (bias, time/freq positional embedding, cls/dist rows) -> fp32 tokens.
+//
+// Replaces PatchEmbed.proj (Conv2d(1, 768, 16, stride), models/passt.py:315,323), the positional adds (:527-529), the
+// Patchout gathers (:535-552: dropped patches are never read) and the cls/dist token assembly (:557-564), and -- when
+// the caller folds spectrogram mixup in (ex_audioset.py:173-177) -- the mix of the two source clips.  The patch rows
+// never exist in HBM: HBM traffic is the kept patches of the mel (read once, through TMA boxes) and the token tensor.
+//
+// Persistent CTAs walk 128-token tiles.  Warp roles (320 threads):
+//   warp 0     : TMA producer: per kept patch one 3-D box [1 clip, 16 mel bins, 16 frames] of fp32 (two boxes with mixup)
+//                into a 2-deep staging ring of 16-patch rounds; conv-weight k-blocks [256 out x 64 k] into a 2-deep ring
+//   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
+//                accumulators double-buffered in TMEM)
+//   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
+//   warps 6-9  : epilogue: tcgen05.ld -> + token table row -> fp32 stores (one full 128-byte line per lane and chunk)
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int kPeThreads = 320;
+constexpr int kPeRound = 16;                 // patches per staging round
+constexpr int kPeRounds = 128 / kPeRound;    // 8 rounds per token tile
+constexpr int kPeDm = 768;
+
+struct PatchEmbedParams {
+  const float* tab;          // [ntok, 768] additive token table
+  float* out;                // [B * ntok, 768]
+  const int* patch_f;        // [ntok - 2]
+  const int* patch_t;
+  const int* mix_perm;       // [B] or nullptr
+  const float* mix_lam;      // [B]
+  int B, ntok, M, m_tiles, fstride, tstride;
+};
+
+struct PatchEmbedSmem {
+  static constexpr int kA = 0;                              // 4 k-block atoms x [128 rows x 128 B] = 64 KB
+  static constexpr int kB = kA + 65536;                     // 2 stages x [256 n x 64 k] bf16 = 64 KB
+  static constexpr int kStage = kB + 65536;                 // 2 buffers x 2 sources x 16 patches x 1 KB = 64 KB
+  static constexpr int kBars = kStage + 65536;
+  static constexpr int kTotal = kBars + 256;
+};
+
+__global__ void __launch_bounds__(kPeThreads, 1)
+patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_constant__ CUtensorMap tmW,
+                   const PatchEmbedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sA = smem + PatchEmbedSmem::kA;
+  uint8_t* sB = smem + PatchEmbedSmem::kB;
+  uint8_t* sStage = smem + PatchEmbedSmem::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PatchEmbedSmem::kBars);
+  uint64_t* st_full = bars;            // [2] staging round landed (TMA tx)
+  uint64_t* st_empty = bars + 2;       // [2] 4 arrivals (converter warps)
+  uint64_t* b_full = bars + 4;         // [2]
+  uint64_t* b_empty = bars + 6;        // [2] tcgen05.commit
+  uint64_t* a_full = bars + 8;         // [1] 4 arrivals: A tile of this token tile is complete
+  uint64_t* a_empty = bars + 9;        // [1] commit after the tile's last MMA
+  uint64_t* t_full = bars + 10;        // [2] accumulator ready
+  uint64_t* t_empty = bars + 12;       // [2] 4 arrivals (epilogue warps)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  int* s_pf = reinterpret_cast<int*>(smem + PatchEmbedSmem::kTotal);   // [ntok - 2] patch rows / columns, staged once
+  int* s_pt = s_pf + (p.ntok - 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool mixing = (p.mix_perm != nullptr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmMel);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4);
+      mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
+      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
+    }
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();
+  for (int i = threadIdx.x; i < p.ntok - 2; i += kPeThreads) {
+    s_pf[i] = p.patch_f[i] * p.fstride;
+    s_pt[i] = p.patch_t[i] * p.tstride;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t rr = 0, bb = 0;       // running staging-round and weight-stage counters
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        // the weight k-blocks of this token tile are requested first where the ring allows, patches in between
+        int wq = 0;                  // weight stages issued for this tile (12 = 3 channel tiles x 4 k-blocks)
+        auto issue_w = [&]() {
+          const uint32_t s = bb & 1;
+          mbar_wait(&b_empty[s], ((bb >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&b_full[s], 256 * 64 * 2);
+          tma_load_2d(sB + s * 32768, &tmW, &b_full[s], (wq & 3) * 64, (wq >> 2) * 256);
+          ++bb; ++wq;
+        };
+        for (int r = 0; r < kPeRounds; ++r, ++rr) {
+          const uint32_t s = rr & 1;
+          mbar_wait(&st_empty[s], ((rr >> 1) & 1) ^ 1);
+          // count the real patches of this round first (cls / dist rows and rows past M are zero-filled by the converter)
+          int n_real = 0;
+          const int row0 = mt * 128 + r * kPeRound;
+          for (int i = 0; i < kPeRound; ++i) {
+            const int row = row0 + i;
+            if (row < p.M && (row % p.ntok) >= 2) ++n_real;
+          }
+          if (n_real == 0) {
+            mbar_arrive(&st_full[s]);
+          } else {
+            mbar_arrive_expect_tx(&st_full[s], uint32_t(n_real) * 1024u * (mixing ? 2u : 1u));
+            for (int i = 0; i < kPeRound; ++i) {
+              const int row = row0 + i;
+              if (row >= p.M) break;
+              const int b = row / p.ntok, n = row - b * p.ntok;
+              if (n < 2) continue;
+              const int f0 = s_pf[n - 2], t0 = s_pt[n - 2];
+              uint8_t* dst = sStage + s * 32768 + i * 1024;
+              tma_load_3d(dst, &tmMel, &st_full[s], t0, f0, b);
+              if (mixing) tma_load_3d(dst + 16384, &tmMel, &st_full[s], t0, f0, __ldg(p.mix_perm + b));
+            }
+          }
+          if (r < 2) issue_w();      // keep the weight ring primed early in the tile
+        }
+        while (wq < 12) issue_w();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+    const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+    uint32_t bb = 0, acc = 0, tiles = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++tiles) {
+      mbar_wait(a_full, tiles & 1);
+      tc_fence_after();
+      for (int nt = 0; nt < 3; ++nt, ++acc) {
+        const uint32_t as = acc & 1;
+        mbar_wait(&t_empty[as], ((acc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 256;
+        for (int kb = 0; kb < 4; ++kb, ++bb) {
+          const uint32_t s = bb & 1;
+          mbar_wait(&b_full[s], (bb >> 1) & 1);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(aA + kb * 16384, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(aB + s * 32768, 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&b_empty[s]);
+            if (kb == 3) {
+              tc_commit(&t_full[as]);
+              if (nt == 2) tc_commit(a_empty);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converter: staging (fp32, 64 B per patch row) -> bf16 A tile =====================
+    const int ct = threadIdx.x - 64;          // 0..127
+    const int pi = ct >> 3;                   // patch inside the round (0..15)
+    const int part = ct & 7;                  // this thread converts patch rows ky = 2*part, 2*part + 1
+    uint32_t rr = 0, tiles = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++tiles) {
+      mbar_wait(a_empty, (tiles & 1) ^ 1);    // the previous tile's MMAs have finished reading A
+      for (int r = 0; r < kPeRounds; ++r, ++rr) {
+        const uint32_t s = rr & 1;
+        mbar_wait(&st_full[s], (rr >> 1) & 1);
+        const int arow = r * kPeRound + pi;   // row inside the 128-token tile
+        const int row = mt * 128 + arow;
+        bool real = false;
+        float lam = 1.f;
+        if (row < p.M) {
+          const int b = row / p.ntok;
+          real = (row - b * p.ntok) >= 2;
+          if (mixing && real) lam = __ldg(p.mix_lam + b);
+        }
+        const float* src = reinterpret_cast<const float*>(sStage + s * 32768 + pi * 1024);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ky = 2 * part + e;
+          float v[16];
+          if (real) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 a = *reinterpret_cast<const float4*>(src + ky * 16 + 4 * i);
+              v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            }
+            if (mixing) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(src + 4096 + ky * 16 + 4 * i);
+                v[4 * i] = v[4 * i] * lam + a.x * (1.0f - lam);
+                v[4 * i + 1] = v[4 * i + 1] * lam + a.y * (1.0f - lam);
+                v[4 * i + 2] = v[4 * i + 2] * lam + a.z * (1.0f - lam);
+                v[4 * i + 3] = v[4 * i + 3] * lam + a.w * (1.0f - lam);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          // k = ky*16 + kx: k-block atom ky/4, 16-byte chunk (ky%4)*2 + kx/8 inside the 128-byte row, XOR-swizzled
+          uint8_t* dst = sA + (ky >> 2) * 16384 + arow * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * h], v[8 * h + 1]); o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
+            o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]); o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+            const int c = (ky & 3) * 2 + h;
+            *reinterpret_cast<uint4*>(dst + ((c ^ (arow & 7)) << 4)) = o;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[s]);    // this warp has read its share of the staging buffer
+      }
+      fence_proxy_async();                           // A tile written by generic stores, read by the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    uint32_t acc = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      const int row = mt * 128 + q * 32 + lane;
+      const bool ok = row < p.M;
+      const float* trow = p.tab + size_t(ok ? row % p.ntok : 0) * kPeDm;
+      float* orow = p.out + size_t(ok ? row : 0) * kPeDm;
+      for (int nt = 0; nt < 3; ++nt, ++acc) {
+        const uint32_t as = acc & 1;
+        mbar_wait(&t_full[as], (acc >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_base + lane_addr + as * 256 + c * 32, v);
+          tmem_ld_wait();
+          if (ok) {
+            const int col = nt * 256 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + col) + i);
+              float4 o;
+              o.x = __uint_as_float(v[4 * i]) + t4.x; o.y = __uint_as_float(v[4 * i + 1]) + t4.y;
+              o.z = __uint_as_float(v[4 * i + 2]) + t4.z; o.w = __uint_as_float(v[4 * i + 3]) + t4.w;
+              reinterpret_cast<float4*>(orow + col)[i] = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace pb
+
+extern "C" {
+
+// mel f32 [B, Fm, Tm]; w_bf16 [768, 256] (conv weight, [out, ky*16+kx]); tab f32 [ntok, 768] (passt_token_table);
+// out f32 [B*ntok, 768].  Returns PB_ERR_BAD_ARG when the mel rows are not 16-byte aligned (Tm % 4 != 0): TMA cannot
+// describe such a tensor and the caller uses passt_im2col + passt_gemm_bf16 instead.
+int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, float* out, const int* patch_f,
+                      const int* patch_t, int B, int ntok, int Fm, int Tm, int fstride, int tstride,
+                      const int* mix_perm, const float* mix_lam, void* stream) {
+  using namespace pb;
+  if (!mel || !w_bf16 || !tab || !out || !patch_f || !patch_t || B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
+  if ((Tm % 4) != 0 || Fm < 16 || Tm < 16 || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(mel) & 15) != 0) return PB_ERR_BAD_ARG;
+  CUtensorMap tmMel, tmW;
+  int rc;
+  if ((rc = make_tmap_3d(&tmMel, mel, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Tm, Fm, B, uint64_t(Tm) * 4,
+                         uint64_t(Fm) * Tm * 4, 16, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
+    return rc;
+  if ((rc = make_tmap_2d(&tmW, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kPeDm, 256, 256 * 2, 256, 64,
+                         CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  PatchEmbedParams p;
+  p.tab = tab; p.out = out; p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
+  p.B = B; p.ntok = ntok; p.M = B * ntok; p.m_tiles = (p.M + 127) / 128; p.fstride = fstride; p.tstride = tstride;
+  const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + size_t(ntok) * 8;
+  if (smem_bytes > 227 * 1024) return PB_ERR_BAD_ARG;
+  PB_SET_SMEM_ONCE(227 * 1024, patch_embed_kernel);
+  const int grid = p.m_tiles < g_sm_limit ? p.m_tiles : g_sm_limit;
+  PB_LAUNCH(patch_embed_kernel, grid, kPeThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream), tmMel, tmW, p);
+  return 0;
+}
+
+}  // extern "C"

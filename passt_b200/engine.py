@@ -189,6 +189,9 @@ B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMaj
 import os as _os
 FUSE_RESID = _os.environ.get("PASST_B200_FUSE_RESID", "1") != "0"
 FUSE_DSUM = _os.environ.get("PASST_B200_FUSE_DSUM", "1") != "0"
+#   PASST_B200_FUSE_PE    : patch embedding as ONE kernel (TMA patch gather -> smem operand -> tcgen05 GEMM -> token table);
+#                           off = passt_im2col (bf16 patch rows in HBM) + the generic GEMM
+FUSE_PE = _os.environ.get("PASST_B200_FUSE_PE", "1") != "0"
 GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
 
 
@@ -373,13 +376,16 @@ class PasstFunction(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         b16 = dict(device=dev, dtype=BF16)
 
-        # ---- patch embedding: im2col of kept patches -> GEMM + token table (bias + pos embeds + cls/dist rows)
-        A0 = torch.empty(M, 256, **b16)
+        # ---- patch embedding: kept patches -> GEMM + token table (bias + pos embeds + cls/dist rows)
         mix_perm = mix_lam = None
         if mix is not None:
             mix_perm, mix_lam = mix
-        L.call("passt_im2col", L.ptr(x32), L.ptr(A0), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, plan.Fm,
-               plan.Tm, fs, ts, L.ptr(mix_perm), L.ptr(mix_lam), st)
+        use_pe = FUSE_PE and plan.Tm % 4 == 0      # TMA needs 16-byte aligned mel rows (e.g. not the 998-frame test shape)
+        A0 = None
+        if not use_pe:
+            A0 = torch.empty(M, 256, **b16)
+            L.call("passt_im2col", L.ptr(x32), L.ptr(A0), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, plan.Fm,
+                   plan.Tm, fs, ts, L.ptr(mix_perm), L.ptr(mix_lam), st)
         tab = torch.empty(ntok, Dm, **f32)
         L.call("passt_token_table", L.ptr(tab), L.ptr(P["cls_token"]), L.ptr(P["dist_token"]),
                L.ptr(P["new_pos_embed"]), L.ptr(P["patch_embed.proj.bias"]), L.ptr(P["time_new_pos_embed"]),
@@ -394,7 +400,11 @@ class PasstFunction(torch.autograd.Function):
             wc.refresh_all([P[n] for n in wnames])
         wpe, _ = wc.get(P["patch_embed.proj.weight"], False)
         xcur = torch.empty(M, Dm, **f32)
-        _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
+        if use_pe:
+            L.call("passt_patch_embed", L.ptr(x32), L.ptr(wpe), L.ptr(tab), L.ptr(xcur), L.ptr(plan.patch_f),
+                   L.ptr(plan.patch_t), B, ntok, plan.Fm, plan.Tm, fs, ts, L.ptr(mix_perm), L.ptr(mix_lam), st)
+        else:
+            _gemm(A0, wpe, xcur, aux=tab, M=M, N=Dm, K=256, lda=256, ldb=256, ldc=Dm, mode=2, period=ntok, ld_aux=Dm)
 
         saved = []
         delta = None
@@ -469,7 +479,7 @@ class PasstFunction(torch.autograd.Function):
             ctx.names = names
             ctx.params = params
             ctx.saved = saved
-            ctx.misc = dict(A0=A0, x_last=xcur, delta_last=delta, fl=fl, M=M, hidden=hidden, C=C, scale=scale)
+            ctx.misc = dict(A0=A0, x32=x32 if A0 is None else None, mix=(mix_perm, mix_lam), x_last=xcur, delta_last=delta, fl=fl, M=M, hidden=hidden, C=C, scale=scale)
         return logits, feats
 
     @staticmethod
@@ -573,7 +583,15 @@ class PasstFunction(torch.autograd.Function):
             chunk_done(pre + "norm1.weight", pre + "mlp.fc2.bias")
         # ---- patch embedding
         gpe = G["patch_embed.proj.weight"].view(Dm, 256)
-        _gemm(gb, mi["A0"], gpe, M=Dm, N=256, K=M, lda=Dm, ldb=256, ldc=256, mode=4, splits=_wgrad_splits(Dm, 256, M, ncl))
+        A0 = mi["A0"]
+        if A0 is None:
+            # the forward never wrote the patch rows to HBM (single-kernel patch embedding): gather them now for the
+            # weight-gradient GEMM (kept patches only, same mixup)
+            A0 = torch.empty(M, 256, **b16)
+            fs, ts = net.stride
+            L.call("passt_im2col", L.ptr(mi["x32"]), L.ptr(A0), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok,
+                   plan.Fm, plan.Tm, fs, ts, L.ptr(mi["mix"][0]), L.ptr(mi["mix"][1]), st)
+        _gemm(gb, A0, gpe, M=Dm, N=256, K=M, lda=Dm, ldb=256, ldc=256, mode=4, splits=_wgrad_splits(Dm, 256, M, ncl))
         L.call("passt_token_table_bwd", L.ptr(g), L.ptr(G["cls_token"]), L.ptr(G["dist_token"]),
                L.ptr(G["new_pos_embed"]), L.ptr(G["patch_embed.proj.bias"]), L.ptr(G["time_new_pos_embed"]),
                L.ptr(G["freq_new_pos_embed"]), L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, Fg, Tg,

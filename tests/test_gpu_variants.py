@@ -122,3 +122,44 @@ def test_fused_residual_and_dsum_switches():
         assert m["relmax"] < 2e-3 and m["cos"] > 0.99999, (k, m)     # same D up to fp32 summation order
         m = grad_metrics(g3[k], g0[k])
         assert m["relmax"] < 1e-2 and m["cos"] > 0.9995, (k, m)
+
+
+@pytest.mark.parametrize("kw,T,mix", [(dict(s_patchout_t=40, s_patchout_f=4), 1000, False), (dict(u_patchout=400), 1000, True),
+                                      (dict(), 1000, False), (dict(s_patchout_t=10, s_patchout_f=3), 500, True),
+                                      (dict(s_patchout_t=40, s_patchout_f=4), 998, False)])
+def test_single_kernel_patch_embed_matches_im2col_gemm(kw, T, mix):
+    """passt_patch_embed (TMA gather + smem operand + tcgen05 GEMM + token table in one kernel) against the two-kernel
+    path (passt_im2col + generic GEMM): same bf16 rounding of the patches, same fp32 accumulation -> logits agree to
+    fp32-summation-order level, gradients (patch rows regathered in backward) too.  T = 998: TMA cannot describe the mel
+    (rows not 16-byte aligned) and the engine must fall back silently to the two-kernel path."""
+    from passt_b200 import engine
+    from passt_b200.passt import get_model, lighten_model
+    torch.manual_seed(0)
+    with quiet():
+        net = lighten_model(get_model(arch="passt_s_swa_p16_128_ap476", pretrained=False, **kw), cut_depth=10)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.01 * torch.randn(p.shape, generator=g))
+    net = net.to(DEV).train()
+    B = 5
+    torch.manual_seed(2)
+    x = torch.randn(B, 1, 128, T, device=DEV)
+    y = (torch.rand(B, 527, device=DEV) < 0.05).float()
+    perm = torch.randperm(B).to(DEV)
+    lam = (torch.rand(B) * 0.5 + 0.5).to(DEV)
+    keep = engine.FUSE_PE
+    res = {}
+    try:
+        for flag in (False, True):
+            engine.FUSE_PE = flag
+            if mix:
+                net.fused_mixup(perm, lam)
+            res[flag] = _run(net, x, y)
+    finally:
+        engine.FUSE_PE = keep
+    (l0, g0), (l1, g1) = res[False], res[True]
+    assert relerr(l1, l0) < 2e-4
+    for k in g0:
+        m = grad_metrics(g1[k], g0[k])
+        assert m["relmax"] < 1e-3 and m["cos"] > 0.99999, (k, m)
