@@ -6,10 +6,10 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/r2_smi.txt 2>&1
-PASST_B200_PDL=0 PASST_B200_ATTN_FWD=1 PASST_B200_FUSE_RESID=0 PASST_B200_FUSE_DSUM=0 \
+PASST_B200_PDL=0 PASST_B200_ATTN_FWD=1 PASST_B200_FUSE_RESID=0 PASST_B200_FUSE_DSUM=0 PASST_B200_FUSE_PE=0 \
   python -m pytest tests -m gpu -q -rA --timeout=1500 --deselect tests/test_gpu_variants.py > $O/r2_pytest_gpu_base.log 2>&1
 echo "pytest exit $?" >> $O/r2_pytest_gpu_base.log
-for t in test_attention_forward_variants_agree test_pdl_on_off_same_results test_fused_residual_and_dsum_switches; do
+for t in test_attention_forward_variants_agree test_pdl_on_off_same_results test_fused_residual_and_dsum_switches test_single_kernel_patch_embed_matches_im2col_gemm; do
   timeout 600 python -m pytest tests/test_gpu_variants.py -m gpu -q -rA -k $t > $O/r2_pytest_variants_$t.log 2>&1
   echo "pytest exit $?" >> $O/r2_pytest_variants_$t.log
 done
@@ -24,7 +24,8 @@ PASST_B200_PDL=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $
 PASST_B200_ATTN_FWD=1 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_attn1.json 2> $O/r2_bench_cfg2_attn1.err
 PASST_B200_FUSE_RESID=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_noresid.json 2> $O/r2_bench_cfg2_noresid.err
 PASST_B200_FUSE_DSUM=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_nodsum.json 2> $O/r2_bench_cfg2_nodsum.err
-PASST_B200_PDL=0 PASST_B200_ATTN_FWD=1 PASST_B200_FUSE_RESID=0 PASST_B200_FUSE_DSUM=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_r1sched.json 2> $O/r2_bench_cfg2_r1sched.err
+PASST_B200_FUSE_PE=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_nope.json 2> $O/r2_bench_cfg2_nope.err
+PASST_B200_PDL=0 PASST_B200_ATTN_FWD=1 PASST_B200_FUSE_RESID=0 PASST_B200_FUSE_DSUM=0 PASST_B200_FUSE_PE=0 timeout 300 python bench.py --steps 20 --warmup 5 --stock 0 > $O/r2_bench_cfg2_r1sched.json 2> $O/r2_bench_cfg2_r1sched.err
 for c in cfg1 cfg3 cfg4 cfg5; do
   timeout 600 python bench.py --config $c --steps 20 --warmup 5 --stock 0 > $O/r2_bench_$c.json 2> $O/r2_bench_$c.err
 done
