@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQKV, const __grid_constant__ CUtensorMap tmdQacc,
                 const AttnBwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sKV = smem + AttnBwdSmem::kKV;
   uint8_t* sQdO = smem + AttnBwdSmem::kQdO;
   uint8_t* sdST = smem + AttnBwdSmem::kdST;
@@ -543,9 +543,9 @@ int passt_attn_bwd_ex(const void* qkv, const void* o, const void* dO, const floa
   p.dq_acc = dq_acc;
   p.dbias = dbias_qkv;
   p.timeline = pb::g_attn_bwd_timeline;
-  PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal, attn_bwd_kernel);
+  PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal + kSmemAlignSlack, attn_bwd_kernel);
   const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
-  PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal, st, tmQKV, tmdO, tmdQKV, tmdQacc, p);
+  PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal + kSmemAlignSlack, st, tmQKV, tmdO, tmdQKV, tmdQacc, p);
   {
     if (C % 256 != 0) return PB_ERR_BAD_ARG;
     const int rows = B * N;

@@ -53,8 +53,8 @@ struct AttnFwdSmem {
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                 const AttnFwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem + AttnFwdSmem::kQ;
   uint8_t* sKV = smem + AttnFwdSmem::kKV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwdSmem::kBars);
@@ -391,9 +391,9 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   p.n_qt = (N + kQTile - 1) / kQTile;
   p.total_items = B * H * p.n_qt;
   p.timeline = pb::g_attn_timeline;
-  PB_SET_SMEM_ONCE(AttnFwdSmem::kTotal, attn_fwd_kernel);
+  PB_SET_SMEM_ONCE(AttnFwdSmem::kTotal + kSmemAlignSlack, attn_fwd_kernel);
   const int grid = p.total_items < 2 * g_sm_limit ? p.total_items : 2 * g_sm_limit;
-  PB_LAUNCH(attn_fwd_kernel, grid, kAttnThreads, AttnFwdSmem::kTotal, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmO, p);
+  PB_LAUNCH(attn_fwd_kernel, grid, kAttnThreads, AttnFwdSmem::kTotal + kSmemAlignSlack, reinterpret_cast<cudaStream_t>(stream), tmQKV, tmO, p);
   return 0;
 }
 

@@ -39,8 +39,8 @@ struct AttnFwd2Smem {
 __global__ void __launch_bounds__(k2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                  const AttnFwd2Params p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sQ = smem + AttnFwd2Smem::kQ;
   uint8_t* sKV = smem + AttnFwd2Smem::kKV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnFwd2Smem::kBars);
@@ -374,9 +374,9 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H
   p.n_qt = (N + k2Tile - 1) / k2Tile;
   p.n_pairs = (p.n_qt + 1) / 2;
   p.total_items = B * H * p.n_pairs;
-  PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal, attn_fwd2_kernel);
+  PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel);
   const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
-  PB_LAUNCH(attn_fwd2_kernel, grid, k2Threads, AttnFwd2Smem::kTotal, st, tmQKV, tmO, p);
+  PB_LAUNCH(attn_fwd2_kernel, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
   return 0;
 }
 

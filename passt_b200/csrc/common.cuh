@@ -42,6 +42,14 @@ constexpr int kNumSMs = 148;
     }                                                                                                       \
   } while (0)
 
+// SWIZZLE_128B TMA / UMMA tiles need 1024-byte aligned shared memory.  The dynamic window of a CTA is only guaranteed
+// to be allocation-unit (128 B) aligned once programmatic dependent launch lets it share an SM with a CTA of the
+// preceding kernel, so kernels align the base themselves (callers add kSmemAlignSlack bytes to the dynamic size).
+constexpr int kSmemAlignSlack = 1024;
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -43,8 +43,8 @@ struct PatchEmbedSmem {
 __global__ void __launch_bounds__(kPeThreads, 1)
 patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_constant__ CUtensorMap tmW,
                    const PatchEmbedParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem + PatchEmbedSmem::kA;
   uint8_t* sB = smem + PatchEmbedSmem::kB;
   uint8_t* sStage = smem + PatchEmbedSmem::kStage;
@@ -295,7 +295,7 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
   PatchEmbedParams p;
   p.tab = tab; p.out = out; p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
   p.B = B; p.ntok = ntok; p.M = B * ntok; p.m_tiles = (p.M + 127) / 128; p.fstride = fstride; p.tstride = tstride;
-  const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + size_t(ntok) * 8;
+  const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + size_t(ntok) * 8 + kSmemAlignSlack;
   if (smem_bytes > 227 * 1024) return PB_ERR_BAD_ARG;
   PB_SET_SMEM_ONCE(227 * 1024, patch_embed_kernel);
   const int grid = p.m_tiles < g_sm_limit ? p.m_tiles : g_sm_limit;

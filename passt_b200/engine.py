@@ -34,6 +34,8 @@ class StepPlan:
     t_keep: Optional[torch.Tensor] = None   # CPU int64 draws (exposed for parity tests)
     f_keep: Optional[torch.Tensor] = None
     u_keep: Optional[torch.Tensor] = None
+    grad_mode: bool = True    # torch.is_grad_enabled() at the call site (Function.forward always runs with it off, and
+                              # ctx.needs_input_grad ignores it): no activations are kept under torch.no_grad()
 
 
 def draw_step_plan(net, x: torch.Tensor, training: bool, static_idx: Optional[torch.Tensor] = None,
@@ -350,7 +352,7 @@ class PasstFunction(torch.autograd.Function):
         M = B * ntok
         Fg, Tg = net.patch_embed.grid_size
         fs, ts = net.stride
-        need_grad = any(ctx.needs_input_grad[4:])   # Function.forward itself runs with grad mode off
+        need_grad = plan.grad_mode and any(ctx.needs_input_grad[4:])
         wc: WeightCache = net._wcache
         if need_grad:
             refresh = True          # an optimizer step may have happened since the last forward (see WeightCache)

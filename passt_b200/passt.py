@@ -243,6 +243,7 @@ class PaSST(nn.Module):
             warnings.warn(f"the patches time dim {t_dim} is larger than the expected time encodings {Tg}, x will be cut")
         with torch.cuda.device(x.device):
             plan = self._preset_plan if self._preset_plan is not None else engine.draw_step_plan(self, x, self.training)
+            plan.grad_mode = torch.is_grad_enabled()
             self.last_plan = plan
             if x.shape[0] == 0:
                 # empty batch: the reference's ops return empty tensors (the random draws above were still consumed)
