@@ -9,6 +9,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from passt_b200.passt import get_model  # noqa: E402
 from passt_b200.preprocess import AugmentMelSTFT  # noqa: E402
+from passt_b200 import loss as PL  # noqa: E402
 
 
 def main():
@@ -28,7 +29,7 @@ def main():
         with torch.no_grad():
             spec = mel(wave).unsqueeze(1)
         logits, _ = net(spec)
-        loss = F.binary_cross_entropy_with_logits(logits, y)
+        loss = PL.bce_with_logits(logits, y)            # fused loss kernel, as bench.py
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
