@@ -649,7 +649,12 @@ def _other_kernel_rooflines(mel, net, wave, B, ntok, peaks):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the cfg2 shape, from the committed ncu --set full
 # summaries under profiles/ (filled in when a capture is committed; None = no capture of the current kernel version)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r2_ncu_kernels_v1.txt (64 clips, N = 474): dram read + write bytes of ONE launch
+    "mel_kernel": 82.47e6 + 9.84e6,                 # algorithmic 114.7 MB (part of the 32.8 MB output is still in L2)
+    "attn_fwd_kernel": 139.85e6 + 25.77e6,          # qkv read once (139.8 MB) + 46.6 MB output (partly L2-resident)
+    "attn_bwd": 282.85e6 + 138.63e6 + 93.21e6 + 4.06e6 + 93.21e6 + 17.38e6,   # main kernel + D pre-pass + dQ pack
+}
 
 
 _REAL_STDOUT_FD = None
