@@ -53,8 +53,8 @@ int main(int argc, char** argv) {
   CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("swz=%d box=%dx%d rank=%d: ENCODE FAILED %d\n", swz, bi, br, rank, (int)r); return 0; }
-  probe<<<1, 128, 65536>>>(tm, o, rank, t0, f0, 1, bytes);
-  cudaError_t e = cudaDeviceSynchronize();
+  probe<<<1, 128, 16384>>>(tm, o, rank, t0, f0, 1, bytes);
+  cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("swz=%d box=%dx%d rank=%d t0=%d: KERNEL ERROR %s\n", swz, bi, br, rank, t0, cudaGetErrorString(e)); return 0; }
   std::vector<float> g(bytes / 4 + 1);
   cudaMemcpy(g.data(), o, bytes + 4, cudaMemcpyDeviceToHost);
