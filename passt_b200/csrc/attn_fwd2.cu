@@ -12,6 +12,7 @@
 // Barriers per side X: s_full[X] (S_X landed), p_full[X] (128 arrivals: P_X written, S_X consumed), pv_done[X]
 // (P_X V accumulated: P_X may be overwritten, O_X may be rescaled / read).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pb {
 
@@ -36,6 +37,9 @@ struct AttnFwd2Smem {
   static constexpr int kTotal = kBars + 256;
 };
 
+// kPrefetch: the TMEM read of score chunk c+1 is issued before chunk c is processed (two register buffers), so the
+// tcgen05.ld round trip is paid once per tile instead of once per 32-column chunk.
+template <bool kPrefetch>
 __global__ void __launch_bounds__(k2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                  const AttnFwd2Params p) {
@@ -257,12 +261,19 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         bool redo = false;
         do {
           float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+          uint32_t vv[kPrefetch ? 2 : 1][32];
+          if (kPrefetch) tmem_ld_x32(tS + lane_addr, vv[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c >= n_chunks) break;
-            uint32_t v[32];
-            tmem_ld_x32(tS + lane_addr + c * 32, v);
-            tmem_ld_wait();
+            if (kPrefetch) {
+              tmem_ld_wait();
+              if (c + 1 < n_chunks) tmem_ld_x32(tS + lane_addr + (c + 1) * 32, vv[(c + 1) & 1]);
+            } else {
+              tmem_ld_x32(tS + lane_addr + c * 32, vv[0]);
+              tmem_ld_wait();
+            }
+            uint32_t (&v)[32] = vv[kPrefetch ? (c & 1) : 0];
             uint32_t pk[16];
             if (full_tile) {
 #pragma unroll
@@ -374,9 +385,18 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H
   p.n_qt = (N + k2Tile - 1) / k2Tile;
   p.n_pairs = (p.n_qt + 1) / 2;
   p.total_items = B * H * p.n_pairs;
-  PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel);
   const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
-  PB_LAUNCH(attn_fwd2_kernel, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
+  static const bool prefetch = [] {
+    const char* e = getenv("PASST_B200_ATTN_PREFETCH");     // default on; 0: one tcgen05.ld round trip per chunk
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (prefetch) {
+    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<true>);
+    PB_LAUNCH(attn_fwd2_kernel<true>, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
+  } else {
+    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<false>);
+    PB_LAUNCH(attn_fwd2_kernel<false>, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
+  }
   return 0;
 }
 

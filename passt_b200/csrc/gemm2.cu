@@ -265,6 +265,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float bias_next = 0.f;
       const bool has_bias = (MODE == kBiasBf16 || MODE == kBiasGeluBf16) && p.bias != nullptr;
       if (has_bias) bias_next = __ldg(p.bias + n_blk * BN + slot * Cfg::kColsPerChunk + lane);
+      // mode 2: the additive operand (token table or residual stream, + bias) of a chunk does not depend on the
+      // accumulator: it is fetched one chunk ahead into registers -- the first chunk's before the wait for the tile --
+      // so that its L2 latency hides behind the previous chunk's TMEM read / staging / store
+      float4 add_next[4];
+      const float* add_row = nullptr;
+      if (MODE == kRowTabF32) {
+        if (row < p.M) add_row = reinterpret_cast<const float*>(p.aux) + size_t(row % p.aux_period) * p.ld_aux + n_blk * BN;
+        const int c0f = slot * Cfg::kColsPerChunk;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add_row != nullptr) a = __ldg(reinterpret_cast<const float4*>(add_row + c0f) + i);
+          if (p.bias != nullptr) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + c0f) + i);
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          }
+          add_next[i] = a;
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
@@ -414,22 +433,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
           if (MODE == kRowTabF32) {
-            if (row < p.M) {
-              const float4* tp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
-                                                                 size_t(row % p.aux_period) * p.ld_aux + col0);
+            float4 add_cur[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) add_cur[i] = add_next[i];
+            const int c0n = c0 + kEpiSlots * Cfg::kColsPerChunk;      // this warp's next chunk of the tile
+            if (c0n < BN) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 t4 = __ldg(tp + i);
-                v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
-              }
-              if (p.bias != nullptr) {
-                const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 b4 = __ldg(bp + i);
-                  v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add_row != nullptr) a = __ldg(reinterpret_cast<const float4*>(add_row + c0n) + i);
+                if (p.bias != nullptr) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + c0n) + i);
+                  a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
                 }
+                add_next[i] = a;
               }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[4 * i] += add_cur[i].x; v[4 * i + 1] += add_cur[i].y;
+              v[4 * i + 2] += add_cur[i].z; v[4 * i + 3] += add_cur[i].w;
             }
           }
           if (lane == 0) tma_store_wait_read<1>();

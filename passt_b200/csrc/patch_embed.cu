@@ -7,8 +7,12 @@
 // never exist in HBM: HBM traffic is the kept patches of the mel (read once, through TMA boxes) and the token tensor.
 //
 // Persistent CTAs walk 128-token tiles.  Warp roles (320 threads):
-//   warp 0     : TMA producer: per kept patch one 3-D box [1 clip, 16 mel bins, 16 frames] of fp32 (two boxes with mixup)
-//                into a 2-deep staging ring of 16-patch rounds; conv-weight k-blocks [256 out x 64 k] into a 2-deep ring
+//   warp 0     : TMA producer: per kept patch one 3-D box [1 clip, 16 mel bins, 20 frames] of fp32 (two boxes with mixup)
+//                into a 2-deep staging ring of 16-patch rounds; conv-weight k-blocks [256 out x 64 k] into a 2-deep ring.
+//                TMA tile loads need a 16-byte aligned start in the contiguous dimension (measured: a box starting at
+//                frame 10 raises an illegal-instruction fault, frames 0/4/8/12 work; tests/probe/tma_probe.cu), and
+//                patch columns start at multiples of the stride (10): the box starts at the frame rounded down to a
+//                multiple of 4 and is 20 frames wide, the converter skips the 0..3 leading frames
 //   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
 //                accumulators double-buffered in TMEM)
 //   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
@@ -21,6 +25,10 @@ constexpr int kPeThreads = 320;
 constexpr int kPeRound = 16;                 // patches per staging round
 constexpr int kPeRounds = 128 / kPeRound;    // 8 rounds per token tile
 constexpr int kPeDm = 768;
+constexpr int kPeBoxW = 20;                  // frames per TMA box: 16 + up to 3 alignment frames, rounded to 16 bytes
+constexpr int kPeSlot = 16 * kPeBoxW * 4;    // 1280 B per staged patch (16 mel rows x 20 frames, fp32)
+constexpr int kPeSrc = kPeRound * kPeSlot;   // 20480 B per source clip and round
+constexpr int kPeBuf = 2 * kPeSrc;           // 40960 B per staging buffer (two sources)
 
 struct PatchEmbedParams {
   const float* tab;          // [ntok, 768] additive token table
@@ -35,8 +43,8 @@ struct PatchEmbedParams {
 struct PatchEmbedSmem {
   static constexpr int kA = 0;                              // 4 k-block atoms x [128 rows x 128 B] = 64 KB
   static constexpr int kB = kA + 65536;                     // 2 stages x [256 n x 64 k] bf16 = 64 KB
-  static constexpr int kStage = kB + 65536;                 // 2 buffers x 2 sources x 16 patches x 1 KB = 64 KB
-  static constexpr int kBars = kStage + 65536;
+  static constexpr int kStage = kB + 65536;                 // 2 buffers x 2 sources x 16 patches x 1280 B = 80 KB
+  static constexpr int kBars = kStage + 2 * kPeBuf;
   static constexpr int kTotal = kBars + 256;
 };
 
@@ -115,16 +123,16 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           if (n_real == 0) {
             mbar_arrive(&st_full[s]);
           } else {
-            mbar_arrive_expect_tx(&st_full[s], uint32_t(n_real) * 1024u * (mixing ? 2u : 1u));
+            mbar_arrive_expect_tx(&st_full[s], uint32_t(n_real) * uint32_t(kPeSlot) * (mixing ? 2u : 1u));
             for (int i = 0; i < kPeRound; ++i) {
               const int row = row0 + i;
               if (row >= p.M) break;
               const int b = row / p.ntok, n = row - b * p.ntok;
               if (n < 2) continue;
-              const int f0 = s_pf[n - 2], t0 = s_pt[n - 2];
-              uint8_t* dst = sStage + s * 32768 + i * 1024;
-              tma_load_3d(dst, &tmMel, &st_full[s], t0, f0, b);
-              if (mixing) tma_load_3d(dst + 16384, &tmMel, &st_full[s], t0, f0, __ldg(p.mix_perm + b));
+              const int f0 = s_pf[n - 2], t0a = s_pt[n - 2] & ~3;     // 16-byte aligned box start
+              uint8_t* dst = sStage + s * kPeBuf + i * kPeSlot;
+              tma_load_3d(dst, &tmMel, &st_full[s], t0a, f0, b);
+              if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], t0a, f0, __ldg(p.mix_perm + b));
             }
           }
           if (r < 2) issue_w();      // keep the weight ring primed early in the tile
@@ -180,31 +188,25 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
         const int row = mt * 128 + arow;
         bool real = false;
         float lam = 1.f;
+        int off = 0;                          // leading alignment frames of this patch's box
         if (row < p.M) {
-          const int b = row / p.ntok;
-          real = (row - b * p.ntok) >= 2;
+          const int b = row / p.ntok, n = row - b * p.ntok;
+          real = n >= 2;
+          if (real) off = s_pt[n - 2] & 3;
           if (mixing && real) lam = __ldg(p.mix_lam + b);
         }
-        const float* src = reinterpret_cast<const float*>(sStage + s * 32768 + pi * 1024);
+        const float* src = reinterpret_cast<const float*>(sStage + s * kPeBuf + pi * kPeSlot) + off;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int ky = 2 * part + e;
           float v[16];
           if (real) {
+            // scalar shared-memory reads: the 0..3 frame offset rules out 16-byte vector loads
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 a = *reinterpret_cast<const float4*>(src + ky * 16 + 4 * i);
-              v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
-            }
+            for (int i = 0; i < 16; ++i) v[i] = src[ky * kPeBoxW + i];
             if (mixing) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 a = *reinterpret_cast<const float4*>(src + 4096 + ky * 16 + 4 * i);
-                v[4 * i] = v[4 * i] * lam + a.x * (1.0f - lam);
-                v[4 * i + 1] = v[4 * i + 1] * lam + a.y * (1.0f - lam);
-                v[4 * i + 2] = v[4 * i + 2] * lam + a.z * (1.0f - lam);
-                v[4 * i + 3] = v[4 * i + 3] * lam + a.w * (1.0f - lam);
-              }
+              for (int i = 0; i < 16; ++i) v[i] = v[i] * lam + src[kPeSrc / 4 + ky * kPeBoxW + i] * (1.0f - lam);
             }
           } else {
 #pragma unroll
@@ -282,12 +284,12 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
                       const int* mix_perm, const float* mix_lam, void* stream) {
   using namespace pb;
   if (!mel || !w_bf16 || !tab || !out || !patch_f || !patch_t || B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
-  if ((Tm % 4) != 0 || Fm < 16 || Tm < 16 || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
+  if ((Tm % 4) != 0 || Fm < 16 || Tm < kPeBoxW || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(mel) & 15) != 0) return PB_ERR_BAD_ARG;
   CUtensorMap tmMel, tmW;
   int rc;
   if ((rc = make_tmap_3d(&tmMel, mel, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Tm, Fm, B, uint64_t(Tm) * 4,
-                         uint64_t(Fm) * Tm * 4, 16, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
+                         uint64_t(Fm) * Tm * 4, kPeBoxW, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
     return rc;
   if ((rc = make_tmap_2d(&tmW, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kPeDm, 256, 256 * 2, 256, 64,
                          CU_TENSOR_MAP_SWIZZLE_128B)))

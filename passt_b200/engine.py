@@ -184,12 +184,12 @@ class WeightCache:
 
 
 B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMajorKN)
-# A/B switches (environment, read once): both default on
+# A/B switches (environment, read once)
 #   PASST_B200_FUSE_RESID : residual adds (x + proj(att), x + fc2(act)) run in the proj / fc2 GEMM epilogues (fp32 output
 #                           = acc + bias + residual); the LayerNorm pass then only reads the fp32 stream
 #   PASST_B200_FUSE_DSUM  : attention backward's D = rowsum(dO o O) is accumulated by the proj-dgrad GEMM epilogue
 import os as _os
-FUSE_RESID = _os.environ.get("PASST_B200_FUSE_RESID", "1") != "0"
+FUSE_RESID = _os.environ.get("PASST_B200_FUSE_RESID", "0") != "0"    # measured: +0.58 ms GEMM epilogue vs -0.48 ms LN
 FUSE_DSUM = _os.environ.get("PASST_B200_FUSE_DSUM", "1") != "0"
 #   PASST_B200_FUSE_PE    : patch embedding as ONE kernel (TMA patch gather -> smem operand -> tcgen05 GEMM -> token table);
 #                           off = passt_im2col (bf16 patch rows in HBM) + the generic GEMM
@@ -382,7 +382,9 @@ class PasstFunction(torch.autograd.Function):
         mix_perm = mix_lam = None
         if mix is not None:
             mix_perm, mix_lam = mix
-        use_pe = FUSE_PE and plan.Tm % 4 == 0      # TMA needs 16-byte aligned mel rows (e.g. not the 998-frame test shape)
+        # TMA needs 16-byte aligned mel rows (not the 998-frame test shape); the kernel stages the patch index list in
+        # shared memory (very long clips fall back to the two-kernel path)
+        use_pe = FUSE_PE and plan.Tm % 4 == 0 and ntok <= 2200
         A0 = None
         if not use_pe:
             A0 = torch.empty(M, 256, **b16)
