@@ -352,7 +352,7 @@ def run_candidate(args, rank, local_rank, world):
             opt = FusedAdamW(opt_params, lr=2e-5, weight_decay=1e-4).attach(net)
         else:
             opt = torch.optim.AdamW(opt_params, lr=2e-5, weight_decay=1e-4, fused=True, capturable=use_graph)
-        reducer = GradAllReducer(net) if world > 1 else None
+        reducer = GradAllReducer(net, reserve_sms=int(os.environ.get("PASST_DDP_RESERVE", "4"))) if world > 1 else None
     torch.manual_seed(1000 + rank)
     # rotating input batches so that consecutive steps never find their input in L2 (>= 4 batches, >= 256 MB in total)
     n_batches = max(4, -(-256 * 2**20 // (B * CLIP_LEN * 4)))
