@@ -703,10 +703,18 @@ def main():
         return
     if world > 1:
         import torch.distributed as dist
+        from passt_b200.ddp import suggest_nccl_ctas
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the gradient all-reduce runs next to persistent 1-CTA-per-SM kernels: give it a few SMs of its own
-        # (passt_b200.ddp.GradAllReducer(reserve_sms=4)) instead of NCCL's default of up to 32 channels
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
+        # the gradient all-reduce runs next to persistent 1-CTA-per-SM kernels: give it SMs of its own
+        # (passt_b200.ddp.GradAllReducer(reserve_sms=...)), as many as the overlap window needs and no more
+        cfg = CONFIGS[args.config]
+        if cfg["kind"] == "train" and "PASST_DDP_RESERVE" not in os.environ:
+            ntok_est = {"cfg2": 474, "cfg3": 790, "cfg5": 353}.get(args.config, 474)
+            bwd_s = (2.0 / 3.0) * 3 * fwd_flops_per_clip(ntok_est, cfg["depth"], cfg["n_classes"]) * \
+                (args.batch or cfg["batch"]) / 750e12
+            n_bytes = 4 * (86.2e6 if cfg["depth"] == 12 else 50.7e6)
+            os.environ["PASST_DDP_RESERVE"] = str(suggest_nccl_ctas(int(n_bytes), world, bwd_s))
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PASST_DDP_RESERVE", "4"))
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
