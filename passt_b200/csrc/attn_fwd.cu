@@ -356,9 +356,11 @@ long long* g_attn_timeline = nullptr;
 
 // attn_fwd2.cu: ping-pong variant (one CTA per SM, two query tiles in flight)
 int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st);
+// attn_fwd3.cu: ping-pong with two softmax threads per query row (16 softmax warps)
+int launch_attn_fwd3(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st);
 int g_attn_fwd_variant = [] {
-  const char* e = getenv("PASST_B200_ATTN_FWD");     // 2 (default): ping-pong kernel; 1: two-CTAs-per-SM kernel
-  return (e != nullptr && e[0] == '1') ? 1 : 2;
+  const char* e = getenv("PASST_B200_ATTN_FWD");     // 2 (default): ping-pong; 3: ping-pong, 2 threads per row; 1: 2 CTAs per SM
+  return (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '3') ? 3 : 2;
 }();
 
 }  // namespace pb
@@ -368,7 +370,7 @@ extern "C" {
 void passt_attn_debug_timeline(void* buf) { pb::g_attn_timeline = reinterpret_cast<long long*>(buf); }
 
 // 2 (default): ping-pong kernel (attn_fwd2.cu); 1: the two-CTAs-per-SM kernel of this file
-void passt_attn_fwd_set_variant(int v) { pb::g_attn_fwd_variant = (v == 1) ? 1 : 2; }
+void passt_attn_fwd_set_variant(int v) { pb::g_attn_fwd_variant = (v == 1 || v == 3) ? v : 2; }
 
 
 // qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, Npad], Npad = 128*ceil(N/128), log2 domain
@@ -377,6 +379,8 @@ int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, 
   if (B <= 0 || N <= 0 || H <= 0) return PB_ERR_BAD_ARG;
   if (g_attn_fwd_variant == 2 && g_attn_timeline == nullptr)
     return launch_attn_fwd2(qkv, out, lse, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
+  if (g_attn_fwd_variant == 3 && g_attn_timeline == nullptr)
+    return launch_attn_fwd3(qkv, out, lse, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
   const int C = H * kHd;
   CUtensorMap tmQKV, tmO;
   int rc;
