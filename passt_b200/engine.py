@@ -186,14 +186,17 @@ class WeightCache:
 B_KN = 16           # passt_gemm_bf16 mode flag: B is [K, N] row-major (kBRowMajorKN)
 # A/B switches (environment, read once)
 #   PASST_B200_FUSE_RESID : residual adds (x + proj(att), x + fc2(act)) run in the proj / fc2 GEMM epilogues (fp32 output
-#                           = acc + bias + residual); the LayerNorm pass then only reads the fp32 stream
+#                           = acc + bias + residual); the LayerNorm pass then only reads the fp32 stream.  Default off:
+#                           the fp32 epilogue (twice the store bytes, 16-column chunks) costs what the LN pass saves.
 #   PASST_B200_FUSE_DSUM  : attention backward's D = rowsum(dO o O) is accumulated by the proj-dgrad GEMM epilogue
 import os as _os
 FUSE_RESID = _os.environ.get("PASST_B200_FUSE_RESID", "0") != "0"    # measured: +0.58 ms GEMM epilogue vs -0.48 ms LN
 FUSE_DSUM = _os.environ.get("PASST_B200_FUSE_DSUM", "1") != "0"
 #   PASST_B200_FUSE_PE    : patch embedding as ONE kernel (TMA patch gather -> smem operand -> tcgen05 GEMM -> token table);
-#                           off = passt_im2col (bf16 patch rows in HBM) + the generic GEMM
-FUSE_PE = _os.environ.get("PASST_B200_FUSE_PE", "1") != "0"
+#                           off (default) = passt_im2col (bf16 patch rows in HBM, kept patches only) + the generic GEMM.
+#                           The single kernel is correct and tested but slower at the bench shape: its TMA boxes are
+#                           16 rows x 80 bytes per patch, and the TMA unit is row-request bound on such short rows.
+FUSE_PE = _os.environ.get("PASST_B200_FUSE_PE", "0") != "0"          # measured: 145 us vs 17 + 43 us (80-byte TMA rows)
 GEMM_TRACE = None   # bench.py sets this to a list to collect (start_event, end_event, flops) per GEMM launch
 
 

@@ -57,7 +57,7 @@ def test_attention_forward_variants_agree(N, ramp):
         assert (got - ref_lse).abs().max().item() < 2e-3 * max(1.0, ref_lse.abs().max().item() / 50), variant
         assert torch.isinf(lse[:, :, N:]).all()
     assert relerr(outs[2][0], outs[1][0]) < 4e-3          # same per-row arithmetic; bf16 output rounding at most
-    assert relerr(outs[3][0], outs[1][0]) < 4e-3
+    assert relerr(outs[3][0], outs[1][0]) < 8e-3          # a side-wide redo moves the reference of rows that did not need it: 1-2 bf16 ulps
 
 
 def _small_train_net(seed=0):
