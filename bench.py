@@ -352,7 +352,7 @@ def run_candidate(args, rank, local_rank, world):
             opt = FusedAdamW(opt_params, lr=2e-5, weight_decay=1e-4).attach(net)
         else:
             opt = torch.optim.AdamW(opt_params, lr=2e-5, weight_decay=1e-4, fused=True, capturable=use_graph)
-        reducer = GradAllReducer(net, reserve_sms=int(os.environ.get("PASST_DDP_RESERVE", "4"))) if world > 1 else None
+        reducer = GradAllReducer(net, reserve_sms=int(os.environ.get("PASST_DDP_RESERVE", "0"))) if world > 1 else None
     torch.manual_seed(1000 + rank)
     # rotating input batches so that consecutive steps never find their input in L2 (>= 4 batches, >= 256 MB in total)
     n_batches = max(4, -(-256 * 2**20 // (B * CLIP_LEN * 4)))
@@ -714,7 +714,8 @@ def main():
                 (args.batch or cfg["batch"]) / 750e12
             n_bytes = 4 * (86.2e6 if cfg["depth"] == 12 else 50.7e6)
             os.environ["PASST_DDP_RESERVE"] = str(suggest_nccl_ctas(int(n_bytes), world, bwd_s))
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PASST_DDP_RESERVE", "4"))
+        if int(os.environ.get("PASST_DDP_RESERVE", "0")) > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["PASST_DDP_RESERVE"])
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

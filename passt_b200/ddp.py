@@ -30,8 +30,10 @@ def suggest_nccl_ctas(n_param_bytes: int, world: int, backward_seconds: float, p
     each GPU's links; one NCCL CTA sustained ~16 GB/s next to the persistent tcgen05 kernels here (measured on 2 x B200:
     345 MB in ~5.5 ms with 4 CTAs).  Too few CTAs expose the all-reduce at small per-GPU batches (cfg5: 67 % weak-scaling
     efficiency with 4), too many take SMs from every backward GEMM (cfg2: 95.0 % with 8 vs 97.0 % with 4).
-    Clamped to [4, 32]."""
-    if world <= 1:
+    Clamped to [4, 32].  With 4 or more ranks NCCL reduces inside the NVSwitch (NVLS, 4 channels) and is fastest left
+    alone: at 8 x B200 the step took 23.63 ms unreserved vs 24.00 / 24.06 / 24.33 ms with 4 / 8 / 16 reserved SMs
+    (profiles/r2_bench_scale8_*.json), so 0 (= no reservation, NCCL's own CTA count) is returned there."""
+    if world <= 1 or world >= 4:
         return 0
     wire = 2.0 * (world - 1) / world * n_param_bytes
     need = wire / (per_cta_gbs * 1e9 * overlap_fraction * max(backward_seconds, 1e-4))
