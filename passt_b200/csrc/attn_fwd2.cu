@@ -39,7 +39,21 @@ struct AttnFwd2Smem {
 
 // kPrefetch: the TMEM read of score chunk c+1 is issued before chunk c is processed (two register buffers), so the
 // tcgen05.ld round trip is paid once per tile instead of once per 32-column chunk.
-template <bool kPrefetch>
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-4 polynomial, relative error ~2e-6 -- far below the bf16
+// rounding of P): used for every 4th score when kPolyExp is set, to take a quarter of the exponentials off the
+// MUFU (XU) pipe, which also serves the bf16 packs.  x <= ~+8 here; very negative x flushes to 0 like ex2.approx.ftz.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);           // f in [-0.5, 0.5]
+  float p = fmaf(f, 9.6181291e-3f, 5.5504109e-2f); // minimax-ish Taylor coefficients of 2^f
+  p = fmaf(p, f, 2.4022651e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // * 2^round(x)
+}
+
+template <bool kPrefetch, bool kPolyExp>
 __global__ void __launch_bounds__(k2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                  const AttnFwd2Params p) {
@@ -282,7 +296,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 mx0 = fmaxf(mx0, s0);
                 mx1 = fmaxf(mx1, s1);
                 const float e0 = ex2_approx(fmaf(s0, p.scale_log2, -m_used));
-                const float e1 = ex2_approx(fmaf(s1, p.scale_log2, -m_used));
+                const float e1 = (kPolyExp && (i & 2)) ? exp2_poly(fmaf(s1, p.scale_log2, -m_used))
+                                                       : ex2_approx(fmaf(s1, p.scale_log2, -m_used));
                 rs0 += e0;
                 rs1 += e1;
                 pk[i >> 1] = pack_bf16(e0, e1);
@@ -390,13 +405,20 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H
     const char* e = getenv("PASST_B200_ATTN_PREFETCH");     // default on; 0: one tcgen05.ld round trip per chunk
     return !(e != nullptr && e[0] == '0');
   }();
-  if (prefetch) {
-    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<true>);
-    PB_LAUNCH(attn_fwd2_kernel<true>, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
-  } else {
-    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<false>);
-    PB_LAUNCH(attn_fwd2_kernel<false>, grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p);
-  }
+  static const bool poly = [] {
+    const char* e = getenv("PASST_B200_ATTN_POLYEXP");      // default off; 1: every 4th exp2 on the FMA pipe
+    return e != nullptr && e[0] == '1';
+  }();
+#define PB_FWD2(PF, PE)                                                                                       \
+  do {                                                                                                        \
+    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<PF, PE>);                       \
+    PB_LAUNCH((attn_fwd2_kernel<PF, PE>), grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p); \
+  } while (0)
+  if (prefetch && poly) PB_FWD2(true, true);
+  else if (prefetch) PB_FWD2(true, false);
+  else if (poly) PB_FWD2(false, true);
+  else PB_FWD2(false, false);
+#undef PB_FWD2
   return 0;
 }
 
