@@ -180,6 +180,27 @@ int passt_gelu_split3(const float* in, void* out_bf16, long long R, int C, void*
 /* residual add + LayerNorm in fp32 with the split operand of the next GEMM as output (models/passt.py:377-380) */
 int passt_ln_fwd_f32tier(const float* x_in, const float* delta_f32, float* x_out, void* h_split_bf16,
                          const float* gamma, const float* beta, int M, int dim, float eps, void* stream);
+/* ---- backward of the fp32 tier (gradients within 1e-3): split products with the contraction along ROWS ------------ */
+/* fp32 [R, C] -> bf16 [3R, C]; pattern 0 = [hi; hi; lo] (A side), 1 = [hi; lo; hi] (B side).  dgrad dX = dY W uses
+ * passt_split3_bf16(dY, pattern 0) x passt_split3_rows_bf16(W, pattern 1) through passt_gemm_bf16 mode 2|16 (fp32 out);
+ * wgrad dW += dY^T X uses rows(dY, 0) x rows(X, 1) through mode 4. */
+int passt_split3_rows_bf16(const float* in, void* out_bf16, long long R, int C, int ld_in, int pattern, void* stream);
+/* bf16 [R, 3C] = [hi|hi|lo] (a forward operand) -> bf16 [3R, C] rows in pattern 0 / 1 */
+int passt_restack3_bf16(const void* in_bf16, void* out_bf16, long long R, int C, int pattern, void* stream);
+/* out[c] += sum_r in[r, c] in fp32 (bias gradients) */
+int passt_colsum_f32(const float* in, float* out, long long R, int C, void* stream);
+/* h = LayerNorm(x) * gamma + beta in fp32 (dim 768) */
+int passt_ln_apply_f32(const float* x, float* h, const float* gamma, const float* beta, int M, int dim, float eps,
+                       void* stream);
+/* g_out = g_in (nullable) + dLN(dh; x, gamma); dgamma / dbeta += (all fp32; autograd of models/passt.py:377-380 norms) */
+int passt_ln_bwd_f32(const float* dh, const float* x, const float* gamma, const float* g_in, float* g_out, float* dgamma,
+                     float* dbeta, int M, int dim, float eps, void* stream);
+/* dpre = dact * gelu'(pre), exact-erf GELU (models/passt.py:280) */
+int passt_gelu_bwd_f32(const float* dact, const float* pre, float* dpre, long long n, void* stream);
+/* attention backward in fp32: qkv f32 [B,N,3C], d_out f32 [B,N,C] -> d_qkv f32 [B,N,3C]; workspace 3*B*H*N floats
+ * (autograd of models/passt.py:345-358) */
+int passt_attn_bwd_f32(const float* qkv, const float* d_out, float* d_qkv, float* workspace, int B, int N, int H,
+                       float scale, void* stream);
 /* passt_im2col with fp32 output rows [B*ntok, 256] (split afterwards) */
 int passt_im2col_f32(const float* mel, float* A_f32, const int* patch_f, const int* patch_t, int B, int ntok, int Fm,
                      int Tm, int fstride, int tstride, const int* mix_perm, const float* mix_lam, void* stream);

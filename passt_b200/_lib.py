@@ -50,6 +50,13 @@ _SIGS = {
     "passt_swa_update": (i32, [vp, i32, i32, C.c_longlong, vp]),
     "passt_wave_augment": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "passt_im2col_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "passt_split3_rows_bf16": (i32, [vp, vp, C.c_longlong, i32, i32, i32, vp]),
+    "passt_restack3_bf16": (i32, [vp, vp, C.c_longlong, i32, i32, vp]),
+    "passt_colsum_f32": (i32, [vp, vp, C.c_longlong, i32, vp]),
+    "passt_ln_apply_f32": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "passt_ln_bwd_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "passt_gelu_bwd_f32": (i32, [vp, vp, vp, C.c_longlong, vp]),
+    "passt_attn_bwd_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "passt_split3_bf16": (i32, [vp, vp, C.c_longlong, i32, i32, i32, vp]),
     "passt_gelu_split3": (i32, [vp, vp, C.c_longlong, i32, vp]),
     "passt_ln_fwd_f32tier": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]),

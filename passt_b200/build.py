@@ -15,13 +15,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpasst_b200.so")
-SOURCES = ["gemm.cu", "gemm2.cu", "mel.cu", "rowops.cu", "attn_fwd.cu", "attn_fwd2.cu", "attn_fwd3.cu", "attn_bwd.cu", "optim.cu", "loss.cu", "waveaug.cu", "fp32tier.cu", "patch_embed.cu"]
+SOURCES = ["gemm.cu", "gemm2.cu", "mel.cu", "rowops.cu", "attn_fwd.cu", "attn_fwd2.cu", "attn_fwd3.cu", "attn_bwd.cu", "optim.cu", "loss.cu", "waveaug.cu", "fp32tier.cu", "fp32tier_bwd.cu", "patch_embed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
 ]
 # --use_fast_math would change logf/erff/div accuracy in the parity-critical kernels; keep IEEE there.
-PRECISE = {"mel.cu", "rowops.cu", "gemm.cu", "gemm2.cu", "attn_fwd.cu", "attn_fwd2.cu", "attn_fwd3.cu", "attn_bwd.cu", "optim.cu", "loss.cu", "waveaug.cu", "fp32tier.cu", "patch_embed.cu"}
+PRECISE = {"mel.cu", "rowops.cu", "gemm.cu", "gemm2.cu", "attn_fwd.cu", "attn_fwd2.cu", "attn_fwd3.cu", "attn_bwd.cu", "optim.cu", "loss.cu", "waveaug.cu", "fp32tier.cu", "fp32tier_bwd.cu", "patch_embed.cu"}
 
 
 def _nvcc() -> str:

@@ -271,7 +271,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float4 add_next[4];
       const float* add_row = nullptr;
       if (MODE == kRowTabF32) {
-        if (row < p.M) add_row = reinterpret_cast<const float*>(p.aux) + size_t(row % p.aux_period) * p.ld_aux + n_blk * BN;
+        if (p.aux != nullptr && row < p.M)
+          add_row = reinterpret_cast<const float*>(p.aux) + size_t(row % p.aux_period) * p.ld_aux + n_blk * BN;
         const int c0f = slot * Cfg::kColsPerChunk;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -586,6 +587,7 @@ int launch_gemm2(int mode, const void* A, const void* B, void* C, void* C2, cons
     case kBiasBf16: return PB_G2(kBiasBf16, false);
     case kBiasGeluBf16: return PB_G2(kBiasGeluBf16, false);
     case kRowTabF32: return PB_G2(kRowTabF32, false);
+    case kRowTabF32 | kBRowMajorKN: return PB_G2(kRowTabF32, true);   // fp32-tier dgrad: B is the row-stacked split weight
     case kGeluGradBf16: return PB_G2(kGeluGradBf16, false);
     case kWgradF32: return PB_G2(kWgradF32, false);
     case kBiasBf16 | kBRowMajorKN: return PB_G2(kBiasBf16, true);

@@ -266,10 +266,18 @@ class SplitWeightCache:
         return ws
 
 
-def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P):
-    """fp32-parity forward (north_star 1e-3 tier; eval / no-grad only): every GEMM runs on the tcgen05 bf16 tensor cores
-    over hi/lo-split operands with a 3x longer contraction and fp32 output (csrc/fp32tier.cu), LayerNorm / GELU /
-    attention / residual stream in fp32."""
+def _split_rows(w2d: torch.Tensor, pattern: int) -> torch.Tensor:
+    """fp32 [R, C] -> bf16 [3R, C] row-stacked split (contraction along rows; csrc/fp32tier_bwd.cu)."""
+    R, C = w2d.shape
+    out = torch.empty(3 * R, C, dtype=BF16, device=w2d.device)
+    L.call("passt_split3_rows_bf16", L.ptr(w2d), L.ptr(out), R, C, w2d.stride(0), pattern, L.stream_ptr())
+    return out
+
+
+def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P, save=None):
+    """fp32-parity forward (north_star 1e-3 tier): every GEMM runs on the tcgen05 bf16 tensor cores over hi/lo-split
+    operands with a 3x longer contraction and fp32 output (csrc/fp32tier.cu), LayerNorm / GELU / attention / residual
+    stream in fp32.  save: dict that receives what the fp32-tier backward needs (None under no_grad)."""
     dev = x32.device
     depth, Dm, H = len(net.blocks), net.embed_dim, net.num_heads
     hidden = P["blocks.0.mlp.fc1.weight"].shape[0] if depth else 4 * Dm
@@ -303,6 +311,7 @@ def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P):
     gemm_f32(A0s, sw.get(P["patch_embed.proj.weight"], refresh), xcur, tab, ntok, Dm, 768)
     delta = None
     scale = float((Dm // H) ** -0.5)
+    blocks_saved = []
     for i in range(depth):
         pre = f"blocks.{i}."
         h1 = torch.empty(M, 3 * Dm, **b16)
@@ -325,6 +334,8 @@ def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P):
         L.call("passt_gelu_split3", L.ptr(pre_act), L.ptr(act), M, hidden, st)
         ofc2 = torch.empty(M, Dm, **f32)
         gemm_f32(act, sw.get(P[pre + "mlp.fc2.weight"], refresh), ofc2, P[pre + "mlp.fc2.bias"], 1, Dm, 3 * hidden)
+        if save is not None:
+            blocks_saved.append(dict(x_in=x_in, h1=h1, qkv=qkv, att=att, x_mid=x_mid, h2=h2, pre_act=pre_act, act=act))
         xcur, delta = x_mid, ofc2
     if delta is not None:
         x_fin = torch.empty(M, Dm, **f32)
@@ -333,10 +344,108 @@ def _forward_fp32_tier(x32, net, plan: StepPlan, mix, P):
     C = P["head.1.weight"].shape[0]
     logits = torch.empty(B, C, **f32)
     feats = torch.empty(B, Dm, **f32)
+    fl = torch.empty(B, Dm, **f32)
     L.call("passt_head_fwd", L.ptr(xcur), None, L.ptr(P["norm.weight"]), L.ptr(P["norm.bias"]),
            L.ptr(P["head.0.weight"]), L.ptr(P["head.0.bias"]), L.ptr(P["head.1.weight"]), L.ptr(P["head.1.bias"]),
-           L.ptr(logits), L.ptr(feats), None, B, ntok, C, st)
+           L.ptr(logits), L.ptr(feats), L.ptr(fl), B, ntok, C, st)
+    if save is not None:
+        save.update(blocks=blocks_saved, A0s=A0s, x_last=xcur, fl=fl, M=M, hidden=hidden, C=C, scale=scale)
     return logits, feats
+
+
+def _backward_fp32_tier(ctx, dlogits, dfeats):
+    """Backward of the fp32 tier: split-operand dgrad / wgrad GEMMs on the tensor cores (contraction 3x longer, fp32
+    output), fp32 LayerNorm / GELU / attention backward (csrc/fp32tier_bwd.cu).  Gradients within 1e-3 of the fp32
+    reference (tests/test_gpu_parity.py::test_fp32_tier_gradients_1e3)."""
+    net, plan, names, params = ctx.net, ctx.plan, ctx.names, ctx.params
+    P = dict(zip(names, params))
+    mi = ctx.misc
+    M, hidden, C, scale = mi["M"], mi["hidden"], mi["C"], mi["scale"]
+    depth, Dm, H = len(net.blocks), net.embed_dim, net.num_heads
+    B, ntok = plan.B, plan.ntok
+    Fg, Tg = net.patch_embed.grid_size
+    dev = mi["x_last"].device
+    st = L.stream_ptr()
+    f32 = dict(device=dev, dtype=torch.float32)
+    b16 = dict(device=dev, dtype=BF16)
+    sizes = [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes), **f32)
+    G, off = {}, 0
+    for n, p, sz in zip(names, params, sizes):
+        G[n] = flat[off: off + sz].view(p.shape)
+        off += sz
+    ncl = L.load().passt_get_sm_limit() // 2
+
+    def dgrad(dy, w, n_out):
+        """dX [M, n_out] = dY [M, K] W [K, n_out] (W = the nn.Linear weight [out=K, in=n_out])."""
+        K = dy.shape[1]
+        a = torch.empty(M, 3 * K, **b16)
+        L.call("passt_split3_bf16", L.ptr(dy), L.ptr(a), M, K, K, 0, st)
+        wr = _split_rows(w.detach().reshape(w.shape[0], -1), 1)              # [3K, n_out]
+        out = torch.empty(M, n_out, **f32)
+        _gemm(a, wr, out, M=M, N=n_out, K=3 * K, lda=3 * K, ldb=n_out, ldc=n_out, mode=2 | B_KN, period=1, ld_aux=n_out)
+        return out
+
+    def wgrad(dy, x_split, gw, n_in):
+        """dW [K_out, n_in] += dY^T [K_out, M] X [M, n_in]; x_split = the forward's column-stacked operand [M, 3 n_in]."""
+        K_out = dy.shape[1]
+        a = _split_rows(dy, 0)                                                # [3M, K_out]
+        xr = torch.empty(3 * M, n_in, **b16)
+        L.call("passt_restack3_bf16", L.ptr(x_split), L.ptr(xr), M, n_in, 1, st)
+        _gemm(a, xr, gw, M=K_out, N=n_in, K=3 * M, lda=K_out, ldb=n_in, ldc=n_in, mode=4,
+              splits=_wgrad_splits(K_out, n_in, 3 * M, ncl))
+
+    def colsum(dy, gb):
+        L.call("passt_colsum_f32", L.ptr(dy), L.ptr(gb), M, dy.shape[1], st)
+
+    dl = torch.zeros(B, C, **f32) if dlogits is None else dlogits.detach().float().contiguous()
+    df = None if dfeats is None else dfeats.detach().float().contiguous()
+    g = torch.zeros(M, Dm, **f32)
+    gb_unused = torch.empty(M, Dm, **b16)
+    L.call("passt_head_bwd", L.ptr(mi["x_last"]), None, L.ptr(P["norm.weight"]), L.ptr(P["norm.bias"]),
+           L.ptr(P["head.0.weight"]), L.ptr(P["head.0.bias"]), L.ptr(P["head.1.weight"]), L.ptr(dl), L.ptr(df),
+           L.ptr(mi["fl"]), L.ptr(g), L.ptr(gb_unused), L.ptr(G["norm.weight"]), L.ptr(G["norm.bias"]),
+           L.ptr(G["head.0.weight"]), L.ptr(G["head.0.bias"]), L.ptr(G["head.1.weight"]), L.ptr(G["head.1.bias"]),
+           None, B, ntok, C, st)
+    ws = torch.empty(3 * B * H * ntok, **f32)
+    for i in reversed(range(depth)):
+        pre = f"blocks.{i}."
+        S = mi["blocks"][i]
+        # ---- MLP: x_next = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+        colsum(g, G[pre + "mlp.fc2.bias"])
+        dact = dgrad(g, P[pre + "mlp.fc2.weight"], hidden)
+        wgrad(g, S["act"], G[pre + "mlp.fc2.weight"], hidden)
+        dpre = torch.empty(M, hidden, **f32)
+        L.call("passt_gelu_bwd_f32", L.ptr(dact), L.ptr(S["pre_act"]), L.ptr(dpre), M * hidden, st)
+        colsum(dpre, G[pre + "mlp.fc1.bias"])
+        dh2 = dgrad(dpre, P[pre + "mlp.fc1.weight"], Dm)
+        wgrad(dpre, S["h2"], G[pre + "mlp.fc1.weight"], Dm)
+        g_mid = torch.empty(M, Dm, **f32)
+        L.call("passt_ln_bwd_f32", L.ptr(dh2), L.ptr(S["x_mid"]), L.ptr(P[pre + "norm2.weight"]), L.ptr(g), L.ptr(g_mid),
+               L.ptr(G[pre + "norm2.weight"]), L.ptr(G[pre + "norm2.bias"]), M, Dm, 1e-6, st)
+        # ---- attention: x_mid = x_in + proj(attn(LN1(x_in)))
+        colsum(g_mid, G[pre + "attn.proj.bias"])
+        datt = dgrad(g_mid, P[pre + "attn.proj.weight"], Dm)
+        wgrad(g_mid, S["att"], G[pre + "attn.proj.weight"], Dm)
+        dqkv = torch.empty(M, 3 * Dm, **f32)
+        L.call("passt_attn_bwd_f32", L.ptr(S["qkv"]), L.ptr(datt), L.ptr(dqkv), L.ptr(ws), B, ntok, H, scale, st)
+        colsum(dqkv, G[pre + "attn.qkv.bias"])
+        dh1 = dgrad(dqkv, P[pre + "attn.qkv.weight"], Dm)
+        wgrad(dqkv, S["h1"], G[pre + "attn.qkv.weight"], Dm)
+        g_new = torch.empty(M, Dm, **f32)
+        L.call("passt_ln_bwd_f32", L.ptr(dh1), L.ptr(S["x_in"]), L.ptr(P[pre + "norm1.weight"]), L.ptr(g_mid),
+               L.ptr(g_new), L.ptr(G[pre + "norm1.weight"]), L.ptr(G[pre + "norm1.bias"]), M, Dm, 1e-6, st)
+        g = g_new
+        mi["blocks"][i] = None
+    # ---- patch embedding
+    wgrad(g, mi["A0s"], G["patch_embed.proj.weight"].view(Dm, 256), 256)
+    L.call("passt_token_table_bwd", L.ptr(g), L.ptr(G["cls_token"]), L.ptr(G["dist_token"]), L.ptr(G["new_pos_embed"]),
+           L.ptr(G["patch_embed.proj.bias"]), L.ptr(G["time_new_pos_embed"]), L.ptr(G["freq_new_pos_embed"]),
+           L.ptr(plan.patch_f), L.ptr(plan.patch_t), B, ntok, Fg, Tg, plan.toffset, L.ptr(plan.toffset_dev), st)
+    net._last_flat_grad = flat
+    ctx.misc = None
+    grads = [G[n] if p.requires_grad else None for n, p in zip(names, params)]
+    return (None, None, None, None, *grads)
 
 
 class PasstFunction(torch.autograd.Function):
@@ -372,8 +481,12 @@ class PasstFunction(torch.autograd.Function):
             raise RuntimeError("passt_b200 supports in_channels == 1 (mono spectrograms)")
         if getattr(net, "precision", "bf16") == "fp32":
             if need_grad:
-                raise RuntimeError("passt_b200: the fp32-parity tier (net.precision = 'fp32') is forward-only; run it "
-                                   "under torch.no_grad() / on parameters that do not require grad, or train in the bf16 tier")
+                wc.gen += 1             # parameters may change before the next forward: the split copies must be rebuilt
+                save = {}
+                out = _forward_fp32_tier(x32, net, plan, mix, P, save)
+                ctx.net, ctx.plan, ctx.names, ctx.params = net, plan, names, params
+                ctx.misc = dict(save, tier="fp32")
+                return out
             wc.dirty = refresh          # the bf16 copies were NOT refreshed by this call: leave their flag as it was
             if refresh:
                 wc.gen -= 1             # (re-setting the flag must not count as a new parameter generation)
@@ -491,6 +604,8 @@ class PasstFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits, dfeats):
+        if ctx.misc.get("tier") == "fp32":
+            return _backward_fp32_tier(ctx, dlogits, dfeats)
         net, plan, names, params = ctx.net, ctx.plan, ctx.names, ctx.params
         P = dict(zip(names, params))
         mi = ctx.misc

@@ -193,7 +193,47 @@ def test_cfg1_fp32_tier_logit_parity_1e3():
     print(f"cfg1 logits relerr: bf16 tier {e_bf16:.2e}, fp32 tier {e_fp32:.2e}; features {relerr(ff, ref_feats):.2e}")
     assert e_fp32 < 1e-3 and relerr(ff, ref_feats) < 1e-3
     assert e_bf16 < 1e-2
-    # the fp32 tier refuses to train instead of silently dropping precision guarantees
-    net.train()
-    with pytest.raises(RuntimeError, match="forward-only"):
-        net(spec)
+
+
+@pytest.mark.parametrize("kw,depth_cut", [(dict(s_patchout_t=40, s_patchout_f=4), 10), (dict(u_patchout=400), 10),
+                                          (dict(s_patchout_t=40, s_patchout_f=4), 0)])
+def test_fp32_tier_gradients_1e3(kw, depth_cut):
+    """north_star's fp32 bound for gradients: net.precision = "fp32" in TRAINING mode (split-operand dgrad / wgrad GEMMs on
+    the tensor cores, fp32 LayerNorm / GELU / attention backward): logits and every parameter gradient within 1e-3
+    (max-norm) of the fp32 CPU oracle, at depth 2 (structured and unstructured patchout) and at full depth."""
+    from util import depth2_params
+    O = _oracle()
+    cfg12 = O.NetCfg(**kw)
+    params12 = O.synth_params(cfg12, seed=3)
+    net = build_net(cfg12, params12, DEV, cut_depth=depth_cut).train()
+    net.precision = "fp32"
+    if depth_cut:
+        cfg = O.NetCfg(depth=2, **kw)
+        p = depth2_params(params12)
+    else:
+        cfg, p = cfg12, params12
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    torch.manual_seed(21)
+    B = 2
+    x = torch.randn(B, 1, 128, 1000)
+    torch.manual_seed(9)
+    logits, feats = net(x.to(DEV))
+    torch.manual_seed(9)
+    d = O.draw_patchout(cfg, 12, 99, True)
+    ref_logits, ref_feats = O.passt_forward(p, x, cfg, d)
+    assert relerr(logits, ref_logits) < 1e-3 and relerr(feats, ref_feats) < 1e-3
+    torch.manual_seed(33)
+    w = torch.randn_like(ref_logits)
+    (ref_logits * w).sum().backward()
+    (logits * w.to(DEV)).sum().backward()
+    got = dict(net.named_parameters())
+    worst = ("", 0.0)
+    for k, v in p.items():
+        if k.startswith("head_dist"):
+            assert got[k].grad is None
+            continue
+        m = grad_metrics(got[k].grad, v.grad)
+        assert m["relmax"] < 1e-3 and m["rel_l2"] < 1e-3 and m["cos"] > 0.999999, (k, m)
+        if m["relmax"] > worst[1]:
+            worst = (k, m["relmax"])
+    print(f"fp32 tier, depth {cfg.depth}: logits {relerr(logits, ref_logits):.2e}, worst gradient {worst[1]:.2e} ({worst[0]})")
