@@ -7,12 +7,14 @@
 // never exist in HBM: HBM traffic is the kept patches of the mel (read once, through TMA boxes) and the token tensor.
 //
 // Persistent CTAs walk 128-token tiles.  Warp roles (320 threads):
-//   warp 0     : TMA producer: per kept patch one 3-D box [1 clip, 16 mel bins, 20 frames] of fp32 (two boxes with mixup)
-//                into a 2-deep staging ring of 16-patch rounds; conv-weight k-blocks [256 out x 64 k] into a 2-deep ring.
+//   warp 0     : TMA producer.  Kept patches are fetched in STRIPS: consecutive tokens of a tile that lie in the same clip and
+//                patch row and whose columns fit a 160-frame window share ONE 3-D box [1 clip, 16 mel bins, 160 frames]
+//                (two boxes with mixup) -- up to 15 patches per box at stride 10 -- into a 3-deep staging ring.  (One box per
+//                patch, 16 rows x 80 bytes, made the TMA unit row-request bound: 145 us vs 60 us for im2col + GEMM.)
 //                TMA tile loads need a 16-byte aligned start in the contiguous dimension (measured: a box starting at
-//                frame 10 raises an illegal-instruction fault, frames 0/4/8/12 work; tests/probe/tma_probe.cu), and
-//                patch columns start at multiples of the stride (10): the box starts at the frame rounded down to a
-//                multiple of 4 and is 20 frames wide, the converter skips the 0..3 leading frames
+//                frame 10 raises an illegal-instruction fault, frames 0/4/8/12 work; tests/probe/tma_probe.cu): a strip
+//                starts at its first patch's frame rounded down to a multiple of 4; the converter applies the offsets.
+//                Conv-weight k-blocks [256 out x 64 k] go into a 2-deep ring
 //   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
 //                accumulators double-buffered in TMEM)
 //   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
@@ -22,13 +24,12 @@
 namespace pb {
 
 constexpr int kPeThreads = 320;
-constexpr int kPeRound = 16;                 // patches per staging round
-constexpr int kPeRounds = 128 / kPeRound;    // 8 rounds per token tile
 constexpr int kPeDm = 768;
-constexpr int kPeBoxW = 20;                  // frames per TMA box: 16 + up to 3 alignment frames, rounded to 16 bytes
-constexpr int kPeSlot = 16 * kPeBoxW * 4;    // 1280 B per staged patch (16 mel rows x 20 frames, fp32)
-constexpr int kPeSrc = kPeRound * kPeSlot;   // 20480 B per source clip and round
-constexpr int kPeBuf = 2 * kPeSrc;           // 40960 B per staging buffer (two sources)
+constexpr int kPeMaxTok = 16;                // patches per strip (8 converter threads each)
+constexpr int kPeSW = 160;                   // frames per strip box
+constexpr int kPeSrc = 16 * kPeSW * 4;       // 10240 B per source clip and strip (16 mel rows x 160 frames, fp32)
+constexpr int kPeBuf = 2 * kPeSrc;           // 20480 B per staging slot (two sources)
+constexpr int kPeSlots = 3;                  // staging ring depth
 
 struct PatchEmbedParams {
   const float* tab;          // [ntok, 768] additive token table
@@ -43,8 +44,9 @@ struct PatchEmbedParams {
 struct PatchEmbedSmem {
   static constexpr int kA = 0;                              // 4 k-block atoms x [128 rows x 128 B] = 64 KB
   static constexpr int kB = kA + 65536;                     // 2 stages x [256 n x 64 k] bf16 = 64 KB
-  static constexpr int kStage = kB + 65536;                 // 2 buffers x 2 sources x 16 patches x 1280 B = 80 KB
-  static constexpr int kBars = kStage + 2 * kPeBuf;
+  static constexpr int kStage = kB + 65536;                 // 3 slots x 2 sources x 10240 B = 60 KB
+  static constexpr int kMeta = kStage + kPeSlots * kPeBuf;  // per slot: {first row in tile, patches, strip start frame, last}
+  static constexpr int kBars = kMeta + 64;
   static constexpr int kTotal = kBars + 256;
 };
 
@@ -57,15 +59,16 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   uint8_t* sB = smem + PatchEmbedSmem::kB;
   uint8_t* sStage = smem + PatchEmbedSmem::kStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PatchEmbedSmem::kBars);
-  uint64_t* st_full = bars;            // [2] staging round landed (TMA tx)
-  uint64_t* st_empty = bars + 2;       // [2] 4 arrivals (converter warps)
-  uint64_t* b_full = bars + 4;         // [2]
-  uint64_t* b_empty = bars + 6;        // [2] tcgen05.commit
-  uint64_t* a_full = bars + 8;         // [1] 4 arrivals: A tile of this token tile is complete
-  uint64_t* a_empty = bars + 9;        // [1] commit after the tile's last MMA
-  uint64_t* t_full = bars + 10;        // [2] accumulator ready
-  uint64_t* t_empty = bars + 12;       // [2] 4 arrivals (epilogue warps)
+  uint64_t* st_full = bars;            // [3] staging strip landed (TMA tx)
+  uint64_t* st_empty = bars + 3;       // [3] 4 arrivals (converter warps)
+  uint64_t* b_full = bars + 6;         // [2]
+  uint64_t* b_empty = bars + 8;        // [2] tcgen05.commit
+  uint64_t* a_full = bars + 10;        // [1] 4 arrivals: A tile of this token tile is complete
+  uint64_t* a_empty = bars + 11;       // [1] commit after the tile's last MMA
+  uint64_t* t_full = bars + 12;        // [2] accumulator ready
+  uint64_t* t_empty = bars + 14;       // [2] 4 arrivals (epilogue warps)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  int4* s_meta = reinterpret_cast<int4*>(smem + PatchEmbedSmem::kMeta);
   int* s_pf = reinterpret_cast<int*>(smem + PatchEmbedSmem::kTotal);   // [ntok - 2] patch rows / columns, staged once
   int* s_pt = s_pf + (p.ntok - 2);
 
@@ -75,8 +78,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmMel);
     tma_prefetch_desc(&tmW);
+    for (int s = 0; s < kPeSlots; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4);
       mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
       mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
     }
@@ -99,9 +102,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t rr = 0, bb = 0;       // running staging-round and weight-stage counters
+      uint32_t ss = 0, bb = 0;       // running staging-strip and weight-stage counters
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        // the weight k-blocks of this token tile are requested first where the ring allows, patches in between
         int wq = 0;                  // weight stages issued for this tile (12 = 3 channel tiles x 4 k-blocks)
         auto issue_w = [&]() {
           const uint32_t s = bb & 1;
@@ -110,33 +112,38 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           tma_load_2d(sB + s * 32768, &tmW, &b_full[s], (wq & 3) * 64, (wq >> 2) * 256);
           ++bb; ++wq;
         };
-        for (int r = 0; r < kPeRounds; ++r, ++rr) {
-          const uint32_t s = rr & 1;
-          mbar_wait(&st_empty[s], ((rr >> 1) & 1) ^ 1);
-          // count the real patches of this round first (cls / dist rows and rows past M are zero-filled by the converter)
-          int n_real = 0;
-          const int row0 = mt * 128 + r * kPeRound;
-          for (int i = 0; i < kPeRound; ++i) {
-            const int row = row0 + i;
-            if (row < p.M && (row % p.ntok) >= 2) ++n_real;
-          }
-          if (n_real == 0) {
+        // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
+        auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
+          const uint32_t s = ss % kPeSlots;
+          mbar_wait(&st_empty[s], ((ss / kPeSlots) & 1) ^ 1);
+          s_meta[s] = make_int4(first, cnt, ws, last);
+          if (cnt == 0) {
             mbar_arrive(&st_full[s]);
           } else {
-            mbar_arrive_expect_tx(&st_full[s], uint32_t(n_real) * uint32_t(kPeSlot) * (mixing ? 2u : 1u));
-            for (int i = 0; i < kPeRound; ++i) {
-              const int row = row0 + i;
-              if (row >= p.M) break;
-              const int b = row / p.ntok, n = row - b * p.ntok;
-              if (n < 2) continue;
-              const int f0 = s_pf[n - 2], t0a = s_pt[n - 2] & ~3;     // 16-byte aligned box start
-              uint8_t* dst = sStage + s * kPeBuf + i * kPeSlot;
-              tma_load_3d(dst, &tmMel, &st_full[s], t0a, f0, b);
-              if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], t0a, f0, __ldg(p.mix_perm + b));
-            }
+            uint8_t* dst = sStage + s * kPeBuf;
+            mbar_arrive_expect_tx(&st_full[s], uint32_t(kPeSrc) * (mixing ? 2u : 1u));
+            tma_load_3d(dst, &tmMel, &st_full[s], ws, f0, b);
+            if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], ws, f0, __ldg(p.mix_perm + b));
           }
-          if (r < 2) issue_w();      // keep the weight ring primed early in the tile
+          ++ss;
+        };
+        const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
+        int r = row0, strips = 0;
+        while (r < row_end) {
+          const int b = r / p.ntok, n = r - b * p.ntok;
+          if (n < 2) { ++r; continue; }                      // cls / dist rows carry no patch
+          const int f0 = s_pf[n - 2], t0 = s_pt[n - 2], ws = t0 & ~3;
+          int cnt = 1;
+          while (cnt < kPeMaxTok && r + cnt < row_end && n + cnt < p.ntok && s_pf[n + cnt - 2] == f0) {
+            const int t2 = s_pt[n + cnt - 2];
+            if (t2 < t0 || t2 + 16 > ws + kPeSW) break;
+            ++cnt;
+          }
+          emit(r - row0, cnt, ws, f0, b, 0);
+          r += cnt;
+          if (++strips <= 2) issue_w();                    // keep the weight ring primed early in the tile
         }
+        emit(0, 0, 0, 0, 0, 1);                            // terminator: the converter closes the tile on it
         while (wq < 12) issue_w();
       }
     }
@@ -176,55 +183,52 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   } else if (warp < 6) {
     // ===================== converter: staging (fp32, 64 B per patch row) -> bf16 A tile =====================
     const int ct = threadIdx.x - 64;          // 0..127
-    const int pi = ct >> 3;                   // patch inside the round (0..15)
-    const int part = ct & 7;                  // this thread converts patch rows ky = 2*part, 2*part + 1
-    uint32_t rr = 0, tiles = 0;
+    const int pi = ct >> 3;                   // patch inside the strip (0..15)
+    const int part = ct & 7;                  // this thread converts patch columns kx = 2*part, 2*part + 1
+    uint32_t ss = 0, tiles = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++tiles) {
       mbar_wait(a_empty, (tiles & 1) ^ 1);    // the previous tile's MMAs have finished reading A
-      for (int r = 0; r < kPeRounds; ++r, ++rr) {
-        const uint32_t s = rr & 1;
-        mbar_wait(&st_full[s], (rr >> 1) & 1);
-        const int arow = r * kPeRound + pi;   // row inside the 128-token tile
-        const int row = mt * 128 + arow;
-        bool real = false;
-        float lam = 1.f;
-        int off = 0;                          // leading alignment frames of this patch's box
-        if (row < p.M) {
-          const int b = row / p.ntok, n = row - b * p.ntok;
-          real = n >= 2;
-          if (real) off = s_pt[n - 2] & 3;
-          if (mixing && real) lam = __ldg(p.mix_lam + b);
+      {
+        // rows without a patch (cls / dist tokens, rows past M) are zero in the operand tile: thread ct owns tile row ct
+        const int row = mt * 128 + ct;
+        if (row >= p.M || (row % p.ntok) < 2) {
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(sA + kb * 16384 + ct * 128 + (c << 4)) = make_uint4(0, 0, 0, 0);
         }
-        const float* src = reinterpret_cast<const float*>(sStage + s * kPeBuf + pi * kPeSlot) + off;
+      }
+      for (;; ++ss) {
+        const uint32_t s = ss % kPeSlots;
+        mbar_wait(&st_full[s], (ss / kPeSlots) & 1);
+        const int4 meta = s_meta[s];          // {first tile row, patches, strip start frame, last}
+        if (pi < meta.y) {
+          const int arow = meta.x + pi;
+          const int row = mt * 128 + arow;
+          const int b = row / p.ntok, n = row - b * p.ntok;
+          const float lam = mixing ? __ldg(p.mix_lam + b) : 1.f;
+          const float* src = reinterpret_cast<const float*>(sStage + s * kPeBuf) + (s_pt[n - 2] - meta.z);
+          // the 8 threads of a patch split its 16 columns (2 each) and walk the 16 rows: neighbouring lanes read
+          // neighbouring frames (bank-conflict free; splitting by rows would put all 8 on one bank, row pitch 160 floats)
+          const int kx = 2 * part;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int ky = 2 * part + e;
-          float v[16];
-          if (real) {
-            // scalar shared-memory reads: the 0..3 frame offset rules out 16-byte vector loads
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = src[ky * kPeBoxW + i];
+          for (int ky = 0; ky < 16; ++ky) {
+            float a0 = src[ky * kPeSW + kx], a1 = src[ky * kPeSW + kx + 1];
             if (mixing) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] * lam + src[kPeSrc / 4 + ky * kPeBoxW + i] * (1.0f - lam);
+              a0 = a0 * lam + src[kPeSrc / 4 + ky * kPeSW + kx] * (1.0f - lam);
+              a1 = a1 * lam + src[kPeSrc / 4 + ky * kPeSW + kx + 1] * (1.0f - lam);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-          }
-          // k = ky*16 + kx: k-block atom ky/4, 16-byte chunk (ky%4)*2 + kx/8 inside the 128-byte row, XOR-swizzled
-          uint8_t* dst = sA + (ky >> 2) * 16384 + arow * 128;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            o.x = pack_bf16(v[8 * h], v[8 * h + 1]); o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
-            o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]); o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
-            const int c = (ky & 3) * 2 + h;
-            *reinterpret_cast<uint4*>(dst + ((c ^ (arow & 7)) << 4)) = o;
+            // k = ky*16 + kx: k-block atom ky/4, 16-byte chunk (ky%4)*2 + kx/8 inside the 128-byte row (XOR-swizzled),
+            // byte (kx%8)*2 inside the chunk
+            const int c = (ky & 3) * 2 + (kx >> 3);
+            *reinterpret_cast<uint32_t*>(sA + (ky >> 2) * 16384 + arow * 128 + ((c ^ (arow & 7)) << 4) + (kx & 7) * 2) =
+                pack_bf16(a0, a1);
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&st_empty[s]);    // this warp has read its share of the staging buffer
+        if (lane == 0) mbar_arrive(&st_empty[s]);    // this warp has read its share of the slot (and its metadata)
+        if (meta.w) { ++ss; break; }
       }
       fence_proxy_async();                           // A tile written by generic stores, read by the tensor core
       __syncwarp();
@@ -284,12 +288,12 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
                       const int* mix_perm, const float* mix_lam, void* stream) {
   using namespace pb;
   if (!mel || !w_bf16 || !tab || !out || !patch_f || !patch_t || B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
-  if ((Tm % 4) != 0 || Fm < 16 || Tm < kPeBoxW || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
+  if ((Tm % 4) != 0 || Fm < 16 || Tm < kPeSW || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(mel) & 15) != 0) return PB_ERR_BAD_ARG;
   CUtensorMap tmMel, tmW;
   int rc;
   if ((rc = make_tmap_3d(&tmMel, mel, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Tm, Fm, B, uint64_t(Tm) * 4,
-                         uint64_t(Fm) * Tm * 4, kPeBoxW, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
+                         uint64_t(Fm) * Tm * 4, kPeSW, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
     return rc;
   if ((rc = make_tmap_2d(&tmW, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kPeDm, 256, 256 * 2, 256, 64,
                          CU_TENSOR_MAP_SWIZZLE_128B)))
