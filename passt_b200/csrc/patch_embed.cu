@@ -18,7 +18,7 @@
 //   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
 //                accumulators double-buffered in TMEM)
 //   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
-//   warps 6-9  : epilogue: tcgen05.ld -> + token table row -> fp32 stores (one full 128-byte line per lane and chunk)
+//   warps 6-9  : epilogue: tcgen05.ld -> transposition pad in shared memory -> + token table row -> coalesced fp32 stores
 #include "common.cuh"
 
 namespace pb {
@@ -47,7 +47,8 @@ struct PatchEmbedSmem {
   static constexpr int kStage = kB + 65536;                 // 3 slots x 2 sources x 10240 B = 60 KB
   static constexpr int kMeta = kStage + kPeSlots * kPeBuf;  // per slot: {first row in tile, patches, strip start frame, last}
   static constexpr int kBars = kMeta + 64;
-  static constexpr int kTotal = kBars + 256;
+  static constexpr int kTrans = kBars + 256;                 // 4 epilogue warps x [32 rows x 33] fp32 transposition pads
+  static constexpr int kTotal = kTrans + 4 * 32 * 33 * 4;
 };
 
 __global__ void __launch_bounds__(kPeThreads, 1)
@@ -236,14 +237,18 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
     }
   } else {
     // ===================== epilogue =====================
+    // tcgen05.ld hands every lane one token row; a [32 x 33] shared-memory pad per warp turns each 32-column chunk
+    // around so that the table reads and the token stores are one full 128-byte line per warp instruction (a lane
+    // walking its own row costs 32 line requests per instruction and made the LSU the kernel's bottleneck).
     const int q = warp & 3;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    float* sT = reinterpret_cast<float*>(smem + PatchEmbedSmem::kTrans) + q * (32 * 33);
     uint32_t acc = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-      const int row = mt * 128 + q * 32 + lane;
-      const bool ok = row < p.M;
-      const float* trow = p.tab + size_t(ok ? row % p.ntok : 0) * kPeDm;
-      float* orow = p.out + size_t(ok ? row : 0) * kPeDm;
+      const int wrow0 = mt * 128 + q * 32;
+      const int my_n = (wrow0 + lane) % p.ntok;                 // token index of the row this lane holds after the ld
+      const int rows = min(32, p.M - wrow0);                    // <= 0: nothing to store for this warp
+      float* obase = p.out + size_t(wrow0) * kPeDm + lane;
       for (int nt = 0; nt < 3; ++nt, ++acc) {
         const uint32_t as = acc & 1;
         mbar_wait(&t_full[as], (acc >> 1) & 1);
@@ -253,17 +258,17 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           uint32_t v[32];
           tmem_ld_x32(tmem_base + lane_addr + as * 256 + c * 32, v);
           tmem_ld_wait();
-          if (ok) {
-            const int col = nt * 256 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + col) + i);
-              float4 o;
-              o.x = __uint_as_float(v[4 * i]) + t4.x; o.y = __uint_as_float(v[4 * i + 1]) + t4.y;
-              o.z = __uint_as_float(v[4 * i + 2]) + t4.z; o.w = __uint_as_float(v[4 * i + 3]) + t4.w;
-              reinterpret_cast<float4*>(orow + col)[i] = o;
-            }
+          for (int i = 0; i < 32; ++i) sT[lane * 33 + i] = __uint_as_float(v[i]);
+          __syncwarp();
+          const int col = nt * 256 + c * 32;
+          const float* tcol = p.tab + col + lane;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int n = __shfl_sync(0xffffffffu, my_n, r);
+            if (r < rows) obase[size_t(r) * kPeDm + col] = sT[r * 33 + lane] + __ldg(tcol + size_t(n) * kPeDm);
           }
+          __syncwarp();
         }
         tc_fence_before();
         __syncwarp();
