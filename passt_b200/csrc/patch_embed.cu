@@ -6,34 +6,33 @@
 // the caller folds spectrogram mixup in (ex_audioset.py:173-177) -- the mix of the two source clips.  The patch rows
 // never exist in HBM: HBM traffic is the kept patches of the mel (read once, through TMA boxes) and the token tensor.
 //
-// Persistent CTAs walk 128-token tiles.  Warp roles (320 threads):
-//   warp 0     : TMA producer.  Kept patches are fetched in STRIPS: consecutive tokens of a tile that lie in the same clip and
-//                patch row and whose columns fit a 160-frame window share ONE 3-D box [1 clip, 16 mel bins, 160 frames]
-//                (two boxes with mixup) -- up to 15 patches per box at stride 10 -- into a 3-deep staging ring.  (One box per
-//                patch, 16 rows x 80 bytes, made the TMA unit row-request bound: 145 us vs 60 us for im2col + GEMM.)
+// Persistent CTAs walk 128-token tiles.  Warp roles (352 threads):
+//   warp 0     : strip producer.  Kept patches are fetched in STRIPS: consecutive tokens of a tile that lie in the same clip
+//                and patch row and whose columns fit a 160-frame window share ONE 3-D box [1 clip, 16 mel bins, 160 frames]
+//                (two boxes with mixup) -- up to 15 patches per box at stride 10 -- into a 3-deep staging ring.
 //                TMA tile loads need a 16-byte aligned start in the contiguous dimension (measured: a box starting at
 //                frame 10 raises an illegal-instruction fault, frames 0/4/8/12 work; tests/probe/tma_probe.cu): a strip
 //                starts at its first patch's frame rounded down to a multiple of 4; the converter applies the offsets.
-//                Conv-weight k-blocks [256 out x 64 k] go into a 2-deep ring
+//   warp 10    : weight producer: conv-weight k-blocks [256 out x 64 k] into a 2-deep ring
 //   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
 //                accumulators double-buffered in TMEM)
 //   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
-//   warps 6-9  : epilogue: tcgen05.ld -> transposition pad in shared memory -> + token table row -> coalesced fp32 stores
+//   warps 6-9  : epilogue: tcgen05.ld + TMA-fetched token-table chunk -> in-place sum -> TMA store (fp32 tokens)
 #include "common.cuh"
 
 namespace pb {
 
-constexpr int kPeThreads = 320;
+constexpr int kPeThreads = 352;
 constexpr int kPeDm = 768;
 constexpr int kPeMaxTok = 16;                // patches per strip (8 converter threads each)
 constexpr int kPeSW = 160;                   // frames per strip box
 constexpr int kPeSrc = 16 * kPeSW * 4;       // 10240 B per source clip and strip (16 mel rows x 160 frames, fp32)
 constexpr int kPeBuf = 2 * kPeSrc;           // 20480 B per staging slot (two sources)
 constexpr int kPeSlots = 3;                  // staging ring depth
+constexpr int kPeEpiSlots = 4;               // per epilogue warp: ring of [32 rows x 16 cols] fp32 buffers
+constexpr int kPeEpiBuf = 32 * 64;
 
 struct PatchEmbedParams {
-  const float* tab;          // [ntok, 768] additive token table
-  float* out;                // [B * ntok, 768]
   const int* patch_f;        // [ntok - 2]
   const int* patch_t;
   const int* mix_perm;       // [B] or nullptr
@@ -45,14 +44,15 @@ struct PatchEmbedSmem {
   static constexpr int kA = 0;                              // 4 k-block atoms x [128 rows x 128 B] = 64 KB
   static constexpr int kB = kA + 65536;                     // 2 stages x [256 n x 64 k] bf16 = 64 KB
   static constexpr int kStage = kB + 65536;                 // 3 slots x 2 sources x 10240 B = 60 KB
-  static constexpr int kMeta = kStage + kPeSlots * kPeBuf;  // per slot: {first row in tile, patches, strip start frame, last}
+  static constexpr int kEpi = kStage + kPeSlots * kPeBuf;   // 4 epilogue warps x 4 x 2 KB = 32 KB
+  static constexpr int kMeta = kEpi + 4 * kPeEpiSlots * kPeEpiBuf;   // per staging slot: {first row, patches, start frame, last}
   static constexpr int kBars = kMeta + 64;
-  static constexpr int kTrans = kBars + 256;                 // 4 epilogue warps x [32 rows x 33] fp32 transposition pads
-  static constexpr int kTotal = kTrans + 4 * 32 * 33 * 4;
+  static constexpr int kTotal = kBars + 512;
 };
 
 __global__ void __launch_bounds__(kPeThreads, 1)
 patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmTab, const __grid_constant__ CUtensorMap tmOut,
                    const PatchEmbedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
@@ -68,10 +68,9 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   uint64_t* a_empty = bars + 11;       // [1] commit after the tile's last MMA
   uint64_t* t_full = bars + 12;        // [2] accumulator ready
   uint64_t* t_empty = bars + 14;       // [2] 4 arrivals (epilogue warps)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* e_full = bars + 16;        // [4 warps][4 slots] token-table chunk landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
   int4* s_meta = reinterpret_cast<int4*>(smem + PatchEmbedSmem::kMeta);
-  int* s_pf = reinterpret_cast<int*>(smem + PatchEmbedSmem::kTotal);   // [ntok - 2] patch rows / columns, staged once
-  int* s_pt = s_pf + (p.ntok - 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool mixing = (p.mix_perm != nullptr);
@@ -79,11 +78,14 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmMel);
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmTab);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < kPeSlots; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
       mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
     }
+    for (int s = 0; s < 16; ++s) mbar_init(&e_full[s], 1);
     mbar_init(a_full, 4);
     mbar_init(a_empty, 1);
     fence_barrier_init();
@@ -94,58 +96,57 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   pdl_gate();
-  for (int i = threadIdx.x; i < p.ntok - 2; i += kPeThreads) {
-    s_pf[i] = p.patch_f[i] * p.fstride;
-    s_pt[i] = p.patch_t[i] * p.tstride;
-  }
-  __syncthreads();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== strip producer =====================
     if (lane == 0) {
-      uint32_t ss = 0, bb = 0;       // running staging-strip and weight-stage counters
+      uint32_t ss = 0;               // running staging-strip counter
+      // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
+      auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
+        const uint32_t s = ss % kPeSlots;
+        mbar_wait(&st_empty[s], ((ss / kPeSlots) & 1) ^ 1);
+        s_meta[s] = make_int4(first, cnt, ws, last);
+        if (cnt == 0) {
+          mbar_arrive(&st_full[s]);
+        } else {
+          uint8_t* dst = sStage + s * kPeBuf;
+          mbar_arrive_expect_tx(&st_full[s], uint32_t(kPeSrc) * (mixing ? 2u : 1u));
+          tma_load_3d(dst, &tmMel, &st_full[s], ws, f0, b);
+          if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], ws, f0, __ldg(p.mix_perm + b));
+        }
+        ++ss;
+      };
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        int wq = 0;                  // weight stages issued for this tile (12 = 3 channel tiles x 4 k-blocks)
-        auto issue_w = [&]() {
+        const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
+        int r = row0;
+        while (r < row_end) {
+          const int b = r / p.ntok, n = r - b * p.ntok;
+          if (n < 2) { ++r; continue; }                      // cls / dist rows carry no patch
+          const int pf0 = __ldg(p.patch_f + n - 2);
+          const int t0 = __ldg(p.patch_t + n - 2) * p.tstride, ws = t0 & ~3;
+          int cnt = 1;
+          while (cnt < kPeMaxTok && r + cnt < row_end && n + cnt < p.ntok && __ldg(p.patch_f + n + cnt - 2) == pf0) {
+            const int t2 = __ldg(p.patch_t + n + cnt - 2) * p.tstride;
+            if (t2 < t0 || t2 + 16 > ws + kPeSW) break;
+            ++cnt;
+          }
+          emit(r - row0, cnt, ws, pf0 * p.fstride, b, 0);
+          r += cnt;
+        }
+        emit(0, 0, 0, 0, 0, 1);                              // terminator: the converter closes the tile on it
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== weight producer: 12 stages [256 out x 64 k] per token tile =====================
+    if (lane == 0) {
+      uint32_t bb = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int wq = 0; wq < 12; ++wq, ++bb) {
           const uint32_t s = bb & 1;
           mbar_wait(&b_empty[s], ((bb >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&b_full[s], 256 * 64 * 2);
           tma_load_2d(sB + s * 32768, &tmW, &b_full[s], (wq & 3) * 64, (wq >> 2) * 256);
-          ++bb; ++wq;
-        };
-        // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
-        auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
-          const uint32_t s = ss % kPeSlots;
-          mbar_wait(&st_empty[s], ((ss / kPeSlots) & 1) ^ 1);
-          s_meta[s] = make_int4(first, cnt, ws, last);
-          if (cnt == 0) {
-            mbar_arrive(&st_full[s]);
-          } else {
-            uint8_t* dst = sStage + s * kPeBuf;
-            mbar_arrive_expect_tx(&st_full[s], uint32_t(kPeSrc) * (mixing ? 2u : 1u));
-            tma_load_3d(dst, &tmMel, &st_full[s], ws, f0, b);
-            if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], ws, f0, __ldg(p.mix_perm + b));
-          }
-          ++ss;
-        };
-        const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
-        int r = row0, strips = 0;
-        while (r < row_end) {
-          const int b = r / p.ntok, n = r - b * p.ntok;
-          if (n < 2) { ++r; continue; }                      // cls / dist rows carry no patch
-          const int f0 = s_pf[n - 2], t0 = s_pt[n - 2], ws = t0 & ~3;
-          int cnt = 1;
-          while (cnt < kPeMaxTok && r + cnt < row_end && n + cnt < p.ntok && s_pf[n + cnt - 2] == f0) {
-            const int t2 = s_pt[n + cnt - 2];
-            if (t2 < t0 || t2 + 16 > ws + kPeSW) break;
-            ++cnt;
-          }
-          emit(r - row0, cnt, ws, f0, b, 0);
-          r += cnt;
-          if (++strips <= 2) issue_w();                    // keep the weight ring primed early in the tile
         }
-        emit(0, 0, 0, 0, 0, 1);                            // terminator: the converter closes the tile on it
-        while (wq < 12) issue_w();
       }
     }
   } else if (warp == 1) {
@@ -209,7 +210,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           const int row = mt * 128 + arow;
           const int b = row / p.ntok, n = row - b * p.ntok;
           const float lam = mixing ? __ldg(p.mix_lam + b) : 1.f;
-          const float* src = reinterpret_cast<const float*>(sStage + s * kPeBuf) + (s_pt[n - 2] - meta.z);
+          const float* src =
+              reinterpret_cast<const float*>(sStage + s * kPeBuf) + (__ldg(p.patch_t + n - 2) * p.tstride - meta.z);
           // the 8 threads of a patch split its 16 columns (2 each) and walk the 16 rows: neighbouring lanes read
           // neighbouring frames (bank-conflict free; splitting by rows would put all 8 on one bank, row pitch 160 floats)
           const int kx = 2 * part;
@@ -236,45 +238,87 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
       if (lane == 0) mbar_arrive(a_full);
     }
   } else {
-    // ===================== epilogue =====================
-    // tcgen05.ld hands every lane one token row; a [32 x 33] shared-memory pad per warp turns each 32-column chunk
-    // around so that the table reads and the token stores are one full 128-byte line per warp instruction (a lane
-    // walking its own row costs 32 line requests per instruction and made the LSU the kernel's bottleneck).
+    // ===================== epilogue (warps 6-9) =====================
+    // Per [32 rows x 16 cols] chunk: the token-table chunk arrives by TMA (SWIZZLE_64B box, prefetched up to three
+    // chunks ahead through a 4-slot ring), the accumulator chunk by tcgen05.ld; the sum overwrites the slot in place and
+    // leaves through a TMA store.  Neither the table read nor the token store costs LSU line requests (a lane walking
+    // its own 3 KB row costs 32 per instruction: 118 us; a padded transposition with coalesced accesses: 221 us).
+    // A warp whose 32 rows cross a clip boundary (token index wraps to 0) fetches a second box at row n0 - ntok (rows
+    // with negative coordinates are zero-filled) and its wrapped lanes read that one.
+    const int ew = warp - 6;
     const int q = warp & 3;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    float* sT = reinterpret_cast<float*>(smem + PatchEmbedSmem::kTrans) + q * (32 * 33);
+    const uint32_t swz = uint32_t((lane >> 1) & 3);
+    uint8_t* ring = smem + PatchEmbedSmem::kEpi + ew * (kPeEpiSlots * kPeEpiBuf);
+    uint64_t* my_full = e_full + ew * kPeEpiSlots;
+    int i_mt = blockIdx.x, i_cc = 0;     // issue iterator (lane 0): next chunk whose table box has not been requested
+    uint32_t is = 0, cs = 0;             // slots requested / slots consumed before the current chunk
+    auto issue_ahead = [&]() {
+      while (i_mt < p.m_tiles) {
+        const int n0 = (i_mt * 128 + q * 32) % p.ntok;
+        const uint32_t need = (n0 + 32 > p.ntok) ? 2u : 1u;
+        if (is + need - cs > uint32_t(kPeEpiSlots)) break;
+        for (uint32_t k = 0; k < need; ++k) {
+          const uint32_t s = (is + k) & 3;
+          mbar_arrive_expect_tx(&my_full[s], kPeEpiBuf);
+          tma_load_2d(ring + s * kPeEpiBuf, &tmTab, &my_full[s], i_cc * 16, k == 0 ? n0 : n0 - p.ntok);
+        }
+        is += need;
+        if (++i_cc == 48) { i_cc = 0; i_mt += gridDim.x; }
+      }
+    };
+    if (lane == 0) issue_ahead();
     uint32_t acc = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       const int wrow0 = mt * 128 + q * 32;
-      const int my_n = (wrow0 + lane) % p.ntok;                 // token index of the row this lane holds after the ld
-      const int rows = min(32, p.M - wrow0);                    // <= 0: nothing to store for this warp
-      float* obase = p.out + size_t(wrow0) * kPeDm + lane;
-      for (int nt = 0; nt < 3; ++nt, ++acc) {
-        const uint32_t as = acc & 1;
-        mbar_wait(&t_full[as], (acc >> 1) & 1);
-        tc_fence_after();
+      const int n0 = wrow0 % p.ntok;
+      const bool wrap = n0 + 32 > p.ntok;
+      const bool from_second = wrap && (n0 + lane >= p.ntok);
+      uint32_t as = 0;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_base + lane_addr + as * 256 + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sT[lane * 33 + i] = __uint_as_float(v[i]);
-          __syncwarp();
-          const int col = nt * 256 + c * 32;
-          const float* tcol = p.tab + col + lane;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int n = __shfl_sync(0xffffffffu, my_n, r);
-            if (r < rows) obase[size_t(r) * kPeDm + col] = sT[r * 33 + lane] + __ldg(tcol + size_t(n) * kPeDm);
-          }
-          __syncwarp();
+      for (int cc = 0; cc < 48; ++cc) {
+        if ((cc & 15) == 0) {
+          as = acc & 1;
+          mbar_wait(&t_full[as], (acc >> 1) & 1);
+          tc_fence_after();
         }
-        tc_fence_before();
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + lane_addr + as * 256 + (cc & 15) * 16, v);
+        if (lane == 0) {
+          tma_store_wait_read<0>();      // every slot but this chunk's has been read by its store: refill them
+          issue_ahead();
+        }
+        const uint32_t s0 = cs & 3, s1 = (cs + 1) & 3;
+        mbar_wait(&my_full[s0], (cs >> 2) & 1);
+        if (wrap) mbar_wait(&my_full[s1], ((cs + 1) >> 2) & 1);
+        tmem_ld_wait();
+        uint8_t* b0 = ring + s0 * kPeEpiBuf;
+        const uint8_t* tsrc = from_second ? ring + s1 * kPeEpiBuf : b0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint32_t off = uint32_t(lane) * 64 + ((uint32_t(ch) ^ swz) << 4);
+          const float4 t4 = *reinterpret_cast<const float4*>(tsrc + off);
+          float4 o;
+          o.x = __uint_as_float(v[4 * ch]) + t4.x; o.y = __uint_as_float(v[4 * ch + 1]) + t4.y;
+          o.z = __uint_as_float(v[4 * ch + 2]) + t4.z; o.w = __uint_as_float(v[4 * ch + 3]) + t4.w;
+          *reinterpret_cast<float4*>(b0 + off) = o;
+        }
+        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[as]);
+        if (lane == 0) {
+          tma_store_2d(&tmOut, b0, cc * 16, wrow0);      // rows past M are clipped by the tensor map
+          tma_store_commit();
+        }
+        cs += wrap ? 2u : 1u;
+        if ((cc & 15) == 15) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[as]);
+          ++acc;
+        }
       }
     }
+    if (lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -295,7 +339,8 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
   if (!mel || !w_bf16 || !tab || !out || !patch_f || !patch_t || B <= 0 || ntok < 2) return PB_ERR_BAD_ARG;
   if ((Tm % 4) != 0 || Fm < 16 || Tm < kPeSW || (mix_perm == nullptr) != (mix_lam == nullptr)) return PB_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(mel) & 15) != 0) return PB_ERR_BAD_ARG;
-  CUtensorMap tmMel, tmW;
+  if (ntok < 32) return PB_ERR_BAD_ARG;          // the epilogue handles at most one clip boundary per 32 rows
+  CUtensorMap tmMel, tmW, tmTab, tmOut;
   int rc;
   if ((rc = make_tmap_3d(&tmMel, mel, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Tm, Fm, B, uint64_t(Tm) * 4,
                          uint64_t(Fm) * Tm * 4, kPeSW, 16, 1, CU_TENSOR_MAP_SWIZZLE_NONE)))
@@ -303,14 +348,22 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
   if ((rc = make_tmap_2d(&tmW, w_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kPeDm, 256, 256 * 2, 256, 64,
                          CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
+  const int Mrows = B * ntok;
+  if ((rc = make_tmap_2d(&tmTab, tab, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ntok, kPeDm, uint64_t(kPeDm) * 4, 32, 16,
+                         CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
+  if ((rc = make_tmap_2d(&tmOut, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Mrows, kPeDm, uint64_t(kPeDm) * 4, 32, 16,
+                         CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
   PatchEmbedParams p;
-  p.tab = tab; p.out = out; p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
+  p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
   p.B = B; p.ntok = ntok; p.M = B * ntok; p.m_tiles = (p.M + 127) / 128; p.fstride = fstride; p.tstride = tstride;
-  const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + size_t(ntok) * 8 + kSmemAlignSlack;
-  if (smem_bytes > 227 * 1024) return PB_ERR_BAD_ARG;
+  const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + kSmemAlignSlack;
+  static_assert(PatchEmbedSmem::kTotal + kSmemAlignSlack <= 227 * 1024, "patch embed shared memory");
   PB_SET_SMEM_ONCE(227 * 1024, patch_embed_kernel);
   const int grid = p.m_tiles < g_sm_limit ? p.m_tiles : g_sm_limit;
-  PB_LAUNCH(patch_embed_kernel, grid, kPeThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream), tmMel, tmW, p);
+  PB_LAUNCH(patch_embed_kernel, grid, kPeThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream), tmMel, tmW, tmTab,
+            tmOut, p);
   return 0;
 }
 
