@@ -75,6 +75,21 @@ def k_ln_bwd():
            L.ptr(gb), L.ptr(dgam), L.ptr(dbet), L.ptr(csum), M, Dm, st)
 
 
+wpe = (0.05 * torch.randn(Dm, 256, device=dev)).bfloat16()
+tab = torch.randn(ntok, Dm, **f32)
+spec32 = spec.contiguous()
+
+
+def k_patch_embed():
+    L.call("passt_patch_embed", L.ptr(spec32), L.ptr(wpe), L.ptr(tab), L.ptr(x_out), L.ptr(plan.patch_f),
+           L.ptr(plan.patch_t), B, ntok, 128, 1000, 10, 10, None, None, st)
+
+
+def k_pe_gemm():
+    L.call("passt_gemm_bf16", L.ptr(A0), L.ptr(wpe), L.ptr(x_out), None, None, L.ptr(tab), M, Dm, 256, 256, 256, Dm,
+           2, ntok, Dm, 1, 0, st)
+
+
 def k_attn_fwd():
     L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(att), L.ptr(lse), B, ntok, H, scale, st)
 
@@ -87,7 +102,11 @@ def k_attn_bwd():
 KERNELS = [("mel", k_mel, B * 1.792e6, "B"), ("im2col", k_im2col, B * ((ntok - 2) * 256 * (4 + 2)), "B"),
            ("ln_fwd", k_ln_fwd, M * Dm * 12.0, "B"), ("ln_bwd", k_ln_bwd, M * Dm * 16.0, "B"),
            ("attn_fwd", k_attn_fwd, 4.0 * B * H * ntok * ntok * 64, "F"),
-           ("attn_bwd", k_attn_bwd, 10.0 * B * H * ntok * ntok * 64, "F")]
+           ("attn_bwd", k_attn_bwd, 10.0 * B * H * ntok * ntok * 64, "F"),
+           ("patch_embed", k_patch_embed, B * (ntok - 2) * 1024.0 + M * Dm * 4.0, "B"),
+           ("pe_gemm", k_pe_gemm, M * 256 * 2.0 + M * Dm * 4.0, "B")]
+if os.environ.get("NCU_ONLY"):
+    KERNELS = [k for k in KERNELS if k[0] in os.environ["NCU_ONLY"].split(",")]
 
 for _, fn, _, _ in KERNELS:          # warm-up (cudaFuncSetAttribute, table builds)
     fn()
