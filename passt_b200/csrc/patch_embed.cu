@@ -33,6 +33,7 @@ constexpr int kPeEpiSlots = 4;               // per epilogue warp: ring of [32 r
 constexpr int kPeEpiBuf = 32 * 64;
 
 struct PatchEmbedParams {
+  const float* tab;          // [ntok, 768] additive token table (also described by tmTab)
   const int* patch_f;        // [ntok - 2]
   const int* patch_t;
   const int* mix_perm;       // [B] or nullptr
@@ -243,80 +244,99 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
     // chunks ahead through a 4-slot ring), the accumulator chunk by tcgen05.ld; the sum overwrites the slot in place and
     // leaves through a TMA store.  Neither the table read nor the token store costs LSU line requests (a lane walking
     // its own 3 KB row costs 32 per instruction: 118 us; a padded transposition with coalesced accesses: 221 us).
-    // A warp whose 32 rows cross a clip boundary (token index wraps to 0) fetches a second box at row n0 - ntok (rows
-    // with negative coordinates are zero-filled) and its wrapped lanes read that one.
     const int ew = warp - 6;
     const int q = warp & 3;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t swz = uint32_t((lane >> 1) & 3);
     uint8_t* ring = smem + PatchEmbedSmem::kEpi + ew * (kPeEpiSlots * kPeEpiBuf);
     uint64_t* my_full = e_full + ew * kPeEpiSlots;
-    int i_mt = blockIdx.x, i_cc = 0;     // issue iterator (lane 0): next chunk whose table box has not been requested
-    uint32_t is = 0, cs = 0;             // slots requested / slots consumed before the current chunk
+    // token index of this warp's first row: (mt * 128 + q * 32) % ntok, advanced tile by tile without divisions (a
+    // single warp per scheduler runs this loop: every dependent instruction's latency is exposed)
+    const int tile_step = (gridDim.x * 128) % p.ntok;
+    int n0 = (blockIdx.x * 128 + q * 32) % p.ntok;
+    // issue iterator (lane 0): next chunk whose table box has not been requested
+    int i_mt = blockIdx.x, i_cc = 0, i_n0 = n0;
+    uint32_t is = 0, cs = 0, cs_prev = 0;   // slots requested / consumed before the current / the previous chunk
     auto issue_ahead = [&]() {
-      while (i_mt < p.m_tiles) {
-        const int n0 = (i_mt * 128 + q * 32) % p.ntok;
-        const uint32_t need = (n0 + 32 > p.ntok) ? 2u : 1u;
-        if (is + need - cs > uint32_t(kPeEpiSlots)) break;
-        for (uint32_t k = 0; k < need; ++k) {
-          const uint32_t s = (is + k) & 3;
-          mbar_arrive_expect_tx(&my_full[s], kPeEpiBuf);
-          tma_load_2d(ring + s * kPeEpiBuf, &tmTab, &my_full[s], i_cc * 16, k == 0 ? n0 : n0 - p.ntok);
+      // slots [cs_prev, is) are busy: the previous chunk's (its store may still be reading it), this chunk's, and the
+      // prefetched ones
+#pragma unroll 1
+      for (int it = 0; it < 2 && i_mt < p.m_tiles; ++it) {
+        if (is + 1u - cs_prev > uint32_t(kPeEpiSlots)) break;
+        const uint32_t s = is & 3;
+        mbar_arrive_expect_tx(&my_full[s], kPeEpiBuf);
+        tma_load_2d(ring + s * kPeEpiBuf, &tmTab, &my_full[s], i_cc * 16, i_n0);   // rows past ntok: zero-filled
+        ++is;
+        if (++i_cc == 48) {
+          i_cc = 0; i_mt += gridDim.x;
+          i_n0 += tile_step;
+          if (i_n0 >= p.ntok) i_n0 -= p.ntok;
         }
-        is += need;
-        if (++i_cc == 48) { i_cc = 0; i_mt += gridDim.x; }
       }
     };
-    if (lane == 0) issue_ahead();
+    if (lane == 0) { issue_ahead(); issue_ahead(); }
     uint32_t acc = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       const int wrow0 = mt * 128 + q * 32;
-      const int n0 = wrow0 % p.ntok;
-      const bool wrap = n0 + 32 > p.ntok;
-      const bool from_second = wrap && (n0 + lane >= p.ntok);
-      uint32_t as = 0;
-#pragma unroll 1
-      for (int cc = 0; cc < 48; ++cc) {
-        if ((cc & 15) == 0) {
-          as = acc & 1;
-          mbar_wait(&t_full[as], (acc >> 1) & 1);
-          tc_fence_after();
-        }
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + lane_addr + as * 256 + (cc & 15) * 16, v);
-        if (lane == 0) {
-          tma_store_wait_read<0>();      // every slot but this chunk's has been read by its store: refill them
-          issue_ahead();
-        }
-        const uint32_t s0 = cs & 3, s1 = (cs + 1) & 3;
-        mbar_wait(&my_full[s0], (cs >> 2) & 1);
-        if (wrap) mbar_wait(&my_full[s1], ((cs + 1) >> 2) & 1);
-        tmem_ld_wait();
-        uint8_t* b0 = ring + s0 * kPeEpiBuf;
-        const uint8_t* tsrc = from_second ? ring + s1 * kPeEpiBuf : b0;
+      // a lane whose row lies past a clip boundary (token index wraps to 0) reads its table row with plain loads, one
+      // chunk ahead; the TMA box zero-fills its rows.  At most one boundary per 32 rows (ntok >= 32)
+      const bool wrapped = n0 + lane >= p.ntok;
+      const float* wrow = p.tab + size_t(wrapped ? n0 + lane - p.ntok : 0) * kPeDm;
+      float4 wnext[4];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t off = uint32_t(lane) * 64 + ((uint32_t(ch) ^ swz) << 4);
-          const float4 t4 = *reinterpret_cast<const float4*>(tsrc + off);
-          float4 o;
-          o.x = __uint_as_float(v[4 * ch]) + t4.x; o.y = __uint_as_float(v[4 * ch + 1]) + t4.y;
-          o.z = __uint_as_float(v[4 * ch + 2]) + t4.z; o.w = __uint_as_float(v[4 * ch + 3]) + t4.w;
-          *reinterpret_cast<float4*>(b0 + off) = o;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOut, b0, cc * 16, wrow0);      // rows past M are clipped by the tensor map
-          tma_store_commit();
-        }
-        cs += wrap ? 2u : 1u;
-        if ((cc & 15) == 15) {
-          tc_fence_before();
+      for (int i = 0; i < 4; ++i) wnext[i] = wrapped ? __ldg(reinterpret_cast<const float4*>(wrow) + i)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int nt = 0; nt < 3; ++nt, ++acc) {
+        const uint32_t as = acc & 1;
+        mbar_wait(&t_full[as], (acc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + as * 256;
+#pragma unroll 1
+        for (int c = 0; c < 16; ++c) {
+          const int col = nt * 256 + c * 16;
+          uint32_t v[16];
+          tmem_ld_x16(taddr + c * 16, v);
+          if (lane == 0) {
+            tma_store_wait_read<1>();    // every store but the previous chunk's has read its slot: refill those
+            issue_ahead();
+          }
+          float4 wcur[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wcur[i] = wnext[i];
+          if (wrapped && col + 16 < kPeDm) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wnext[i] = __ldg(reinterpret_cast<const float4*>(wrow + col + 16) + i);
+          }
+          const uint32_t s0 = cs & 3;
+          uint8_t* b0 = ring + s0 * kPeEpiBuf;
+          mbar_wait(&my_full[s0], (cs >> 2) & 1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t off = uint32_t(lane) * 64 + ((uint32_t(ch) ^ swz) << 4);
+            const float4 s4 = *reinterpret_cast<const float4*>(b0 + off);
+            const float4 t4 = wrapped ? wcur[ch] : s4;
+            float4 o;
+            o.x = __uint_as_float(v[4 * ch]) + t4.x; o.y = __uint_as_float(v[4 * ch + 1]) + t4.y;
+            o.z = __uint_as_float(v[4 * ch + 2]) + t4.z; o.w = __uint_as_float(v[4 * ch + 3]) + t4.w;
+            *reinterpret_cast<float4*>(b0 + off) = o;
+          }
+          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[as]);
-          ++acc;
+          if (lane == 0) {
+            tma_store_2d(&tmOut, b0, col, wrow0);      // rows past M are clipped by the tensor map
+            tma_store_commit();
+          }
+          cs_prev = cs;
+          ++cs;
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
       }
+      n0 += tile_step;
+      if (n0 >= p.ntok) n0 -= p.ntok;
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -356,7 +376,7 @@ int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, fl
                          CU_TENSOR_MAP_SWIZZLE_64B)))
     return rc;
   PatchEmbedParams p;
-  p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
+  p.tab = tab; p.patch_f = patch_f; p.patch_t = patch_t; p.mix_perm = mix_perm; p.mix_lam = mix_lam;
   p.B = B; p.ntok = ntok; p.M = B * ntok; p.m_tiles = (p.M + 127) / 128; p.fstride = fstride; p.tstride = tstride;
   const size_t smem_bytes = size_t(PatchEmbedSmem::kTotal) + kSmemAlignSlack;
   static_assert(PatchEmbedSmem::kTotal + kSmemAlignSlack <= 227 * 1024, "patch embed shared memory");

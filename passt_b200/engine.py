@@ -500,7 +500,7 @@ class PasstFunction(torch.autograd.Function):
             mix_perm, mix_lam = mix
         # TMA needs 16-byte aligned mel rows (not the 998-frame test shape); the kernel stages the patch index list in
         # shared memory (very long clips fall back to the two-kernel path)
-        use_pe = FUSE_PE and plan.Tm % 4 == 0 and plan.Tm >= 160 and ntok <= 2200
+        use_pe = FUSE_PE and plan.Tm % 4 == 0 and plan.Tm >= 160 and ntok >= 32
         A0 = None
         if not use_pe:
             A0 = torch.empty(M, 256, **b16)

@@ -39,6 +39,6 @@ def run(B, Fg, Tg, T, mix):
     print(f"B={B} grid={Fg}x{Tg} ntok={ntok} T={T} mix={mix}: relerr {err:.2e}", flush=True)
 
 
-for args in [(1, 2, 3, 160, False), (1, 12, 10, 200, False), (2, 12, 20, 256, False), (3, 8, 59, 1000, True), (5, 12, 99, 1000, False)]:
+for args in [(1, 4, 10, 160, False), (1, 12, 10, 200, False), (2, 12, 20, 256, False), (3, 8, 59, 1000, True), (5, 12, 99, 1000, False)]:
     run(*args)
 print("done")
