@@ -95,7 +95,8 @@ int passt_im2col(const float* mel, void* A_bf16, const int* patch_f, const int* 
 /* single-kernel patch embedding: TMA gather of the kept 16x16 patches (optionally mixing two clips) -> bf16 operand
  * tile in shared memory -> tcgen05 GEMM with the conv weight w_bf16 [768, 256] -> + token table -> f32 [B*ntok, 768]
  * (PatchEmbed.proj + positional adds + Patchout + token assembly, models/passt.py:315-323,527-564).  Returns a
- * negative code when Tm % 4 != 0 (TMA needs 16-byte aligned mel rows): use passt_im2col + passt_gemm_bf16 then. */
+ * negative code when Tm % 4 != 0 (TMA needs 16-byte aligned mel rows), Tm < 160 (one strip box) or ntok < 32: use
+ * passt_im2col + passt_gemm_bf16 then. */
 int passt_patch_embed(const float* mel, const void* w_bf16, const float* tab, float* out, const int* patch_f,
                       const int* patch_t, int B, int ntok, int Fm, int Tm, int fstride, int tstride,
                       const int* mix_perm, const float* mix_lam, void* stream);

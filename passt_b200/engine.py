@@ -498,8 +498,8 @@ class PasstFunction(torch.autograd.Function):
         mix_perm = mix_lam = None
         if mix is not None:
             mix_perm, mix_lam = mix
-        # TMA needs 16-byte aligned mel rows (not the 998-frame test shape); the kernel stages the patch index list in
-        # shared memory (very long clips fall back to the two-kernel path)
+        # TMA needs 16-byte aligned mel rows (not the 998-frame test shape) and a clip at least one strip box long; the
+        # epilogue handles at most one clip boundary per 32 token rows
         use_pe = FUSE_PE and plan.Tm % 4 == 0 and plan.Tm >= 160 and ntok >= 32
         A0 = None
         if not use_pe:
