@@ -6,7 +6,7 @@
 // the caller folds spectrogram mixup in (ex_audioset.py:173-177) -- the mix of the two source clips.  The patch rows
 // never exist in HBM: HBM traffic is the kept patches of the mel (read once, through TMA boxes) and the token tensor.
 //
-// Persistent CTAs walk 128-token tiles.  Warp roles (352 threads):
+// Persistent CTAs walk 128-token tiles.  Warp roles (480 threads):
 //   warp 0     : strip producer.  Kept patches are fetched in STRIPS: consecutive tokens of a tile that lie in the same clip
 //                and patch row and whose columns fit a 160-frame window share ONE 3-D box [1 clip, 16 mel bins, 160 frames]
 //                (two boxes with mixup) -- up to 15 patches per box at stride 10 -- into a 3-deep staging ring.
@@ -17,12 +17,15 @@
 //   warp 1     : tcgen05.mma issuer (M = 128 tokens, N = 256 channels, K = 256 taps; 3 channel tiles per token tile,
 //                accumulators double-buffered in TMEM)
 //   warps 2-5  : converter: staged fp32 patches (x lam + partner x (1 - lam)) -> bf16 -> K-major SWIZZLE_128B A tile
-//   warps 6-9  : epilogue: tcgen05.ld + TMA-fetched token-table chunk -> in-place sum -> TMA store (fp32 tokens)
+//   warps 6-9  : epilogue: tcgen05.ld + TMA-fetched token-table chunk -> in-place sum in shared memory
+//   warps 11-14: one helper lane per epilogue warp: token-table chunk requests and TMA stores of the sums (fp32 tokens)
 #include "common.cuh"
+
+#include <type_traits>
 
 namespace pb {
 
-constexpr int kPeThreads = 352;
+constexpr int kPeThreads = 480;
 constexpr int kPeDm = 768;
 constexpr int kPeMaxTok = 16;                // patches per strip (8 converter threads each)
 constexpr int kPeSW = 160;                   // frames per strip box
@@ -31,6 +34,15 @@ constexpr int kPeBuf = 2 * kPeSrc;           // 20480 B per staging slot (two so
 constexpr int kPeSlots = 3;                  // staging ring depth
 constexpr int kPeEpiSlots = 4;               // per epilogue warp: ring of [32 rows x 16 cols] fp32 buffers
 constexpr int kPeEpiBuf = 32 * 64;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 struct PatchEmbedParams {
   const float* tab;          // [ntok, 768] additive token table (also described by tmTab)
@@ -69,8 +81,9 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   uint64_t* a_empty = bars + 11;       // [1] commit after the tile's last MMA
   uint64_t* t_full = bars + 12;        // [2] accumulator ready
   uint64_t* t_empty = bars + 14;       // [2] 4 arrivals (epilogue warps)
-  uint64_t* e_full = bars + 16;        // [4 warps][4 slots] token-table chunk landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
+  uint64_t* e_full = bars + 16;        // [4 warps][4 slots] token-table chunk landed (TMA tx)
+  uint64_t* e_ready = bars + 32;       // [4 warps][4 slots] sum written into the slot (1 arrival, epilogue lane 0)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 48);
   int4* s_meta = reinterpret_cast<int4*>(smem + PatchEmbedSmem::kMeta);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +99,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
       mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
       mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
     }
-    for (int s = 0; s < 16; ++s) mbar_init(&e_full[s], 1);
+    for (int s = 0; s < 16; ++s) { mbar_init(&e_full[s], 1); mbar_init(&e_ready[s], 1); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 1);
     fence_barrier_init();
@@ -238,31 +251,101 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue (warps 6-9) =====================
-    // Per [32 rows x 16 cols] chunk: the token-table chunk arrives by TMA (SWIZZLE_64B box, prefetched up to three
-    // chunks ahead through a 4-slot ring), the accumulator chunk by tcgen05.ld; the sum overwrites the slot in place and
-    // leaves through a TMA store.  Neither the table read nor the token store costs LSU line requests (a lane walking
-    // its own 3 KB row costs 32 per instruction: 118 us; a padded transposition with coalesced accesses: 221 us).
+    // Per [32 rows x 16 cols] chunk: the token-table chunk arrives by TMA (SWIZZLE_64B box, requested by this warp's
+    // helper up to three chunks ahead through a 4-slot ring), the accumulator chunk by tcgen05.ld; the sum overwrites the
+    // slot in place and the helper stores it by TMA.  Neither the table read nor the token store costs LSU line requests
+    // (a lane walking its own 3 KB row costs 32 per instruction: 118 us; a padded transposition with coalesced accesses:
+    // 221 us), and the TMA bookkeeping is off this warp: one warp per scheduler exposes every instruction's latency
+    // (~1000 clk per chunk with the bookkeeping inline: 92 us).
     const int ew = warp - 6;
     const int q = warp & 3;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t swz = uint32_t((lane >> 1) & 3);
-    uint8_t* ring = smem + PatchEmbedSmem::kEpi + ew * (kPeEpiSlots * kPeEpiBuf);
+    const uint32_t ring = smem_u32(smem + PatchEmbedSmem::kEpi + ew * (kPeEpiSlots * kPeEpiBuf));
     uint64_t* my_full = e_full + ew * kPeEpiSlots;
-    // token index of this warp's first row: (mt * 128 + q * 32) % ntok, advanced tile by tile without divisions (a
-    // single warp per scheduler runs this loop: every dependent instruction's latency is exposed)
+    uint64_t* my_ready = e_ready + ew * kPeEpiSlots;
+    uint32_t off[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) off[ch] = uint32_t(lane) * 64 + ((uint32_t(ch) ^ swz) << 4);
     const int tile_step = (gridDim.x * 128) % p.ntok;
-    int n0 = (blockIdx.x * 128 + q * 32) % p.ntok;
-    // issue iterator (lane 0): next chunk whose table box has not been requested
-    int i_mt = blockIdx.x, i_cc = 0, i_n0 = n0;
-    uint32_t is = 0, cs = 0, cs_prev = 0;   // slots requested / consumed before the current / the previous chunk
-    auto issue_ahead = [&]() {
-      // slots [cs_prev, is) are busy: the previous chunk's (its store may still be reading it), this chunk's, and the
-      // prefetched ones
+    int n0 = (blockIdx.x * 128 + q * 32) % p.ntok;     // token index of this warp's first row
+    uint32_t acc = 0, cs = 0;
+    // one accumulator tile (16 chunks); kWrap: this warp's rows cross a clip boundary (token index wraps to 0) -- the TMA
+    // box zero-fills the rows past ntok and those lanes read their table row with plain loads, one chunk ahead
+    auto run_ntile = [&](auto wrap_tag, int nt, uint32_t taddr, const float* wrow, bool wrapped) {
+      constexpr bool kWrap = decltype(wrap_tag)::value;
+      float4 wnext[4];
+      if (kWrap) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          wnext[i] = wrapped ? __ldg(reinterpret_cast<const float4*>(wrow + nt * 256) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll 1
-      for (int it = 0; it < 2 && i_mt < p.m_tiles; ++it) {
-        if (is + 1u - cs_prev > uint32_t(kPeEpiSlots)) break;
+      for (int c = 0; c < 16; ++c, ++cs) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c * 16, v);
+        float4 wcur[4];
+        if (kWrap) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wcur[i] = wnext[i];
+          if (wrapped && c < 15) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              wnext[i] = __ldg(reinterpret_cast<const float4*>(wrow + nt * 256 + (c + 1) * 16) + i);
+          }
+        }
+        const uint32_t s0 = cs & 3;
+        const uint32_t b0 = ring + s0 * kPeEpiBuf;
+        mbar_wait(&my_full[s0], (cs >> 2) & 1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float4 t4 = lds128(b0 + off[ch]);
+          if (kWrap) { if (wrapped) t4 = wcur[ch]; }
+          float4 o;
+          o.x = __uint_as_float(v[4 * ch]) + t4.x; o.y = __uint_as_float(v[4 * ch + 1]) + t4.y;
+          o.z = __uint_as_float(v[4 * ch + 2]) + t4.z; o.w = __uint_as_float(v[4 * ch + 3]) + t4.w;
+          sts128(b0 + off[ch], o);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&my_ready[s0]);
+      }
+    };
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      const bool wrap = n0 + 32 > p.ntok;                 // warp-uniform
+      const bool wrapped = n0 + lane >= p.ntok;
+      const float* wrow = p.tab + size_t(wrapped ? n0 + lane - p.ntok : 0) * kPeDm;
+#pragma unroll 1
+      for (int nt = 0; nt < 3; ++nt, ++acc) {
+        const uint32_t as = acc & 1;
+        mbar_wait(&t_full[as], (acc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + as * 256;
+        if (wrap) run_ntile(std::true_type{}, nt, taddr, wrow, wrapped);
+        else run_ntile(std::false_type{}, nt, taddr, wrow, false);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
+      }
+      n0 += tile_step;
+      if (n0 >= p.ntok) n0 -= p.ntok;
+    }
+  } else {
+    // ===================== epilogue helpers (warps 11-14, one lane each): table-chunk requests and token stores =========
+    if (lane == 0) {
+      const int ew = warp - 11;
+      const int q = (ew + 6) & 3;                          // TMEM quadrant of epilogue warp 6 + ew
+      uint8_t* ring = smem + PatchEmbedSmem::kEpi + ew * (kPeEpiSlots * kPeEpiBuf);
+      uint64_t* my_full = e_full + ew * kPeEpiSlots;
+      uint64_t* my_ready = e_ready + ew * kPeEpiSlots;
+      const int tile_step = (gridDim.x * 128) % p.ntok;
+      // request iterator: next chunk whose table box has not been requested
+      int i_mt = blockIdx.x, i_cc = 0, i_n0 = (blockIdx.x * 128 + q * 32) % p.ntok;
+      uint32_t is = 0, cs = 0;
+      auto request = [&]() {
         const uint32_t s = is & 3;
         mbar_arrive_expect_tx(&my_full[s], kPeEpiBuf);
         tma_load_2d(ring + s * kPeEpiBuf, &tmTab, &my_full[s], i_cc * 16, i_n0);   // rows past ntok: zero-filled
@@ -272,73 +355,23 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           i_n0 += tile_step;
           if (i_n0 >= p.ntok) i_n0 -= p.ntok;
         }
-      }
-    };
-    if (lane == 0) { issue_ahead(); issue_ahead(); }
-    uint32_t acc = 0;
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-      const int wrow0 = mt * 128 + q * 32;
-      // a lane whose row lies past a clip boundary (token index wraps to 0) reads its table row with plain loads, one
-      // chunk ahead; the TMA box zero-fills its rows.  At most one boundary per 32 rows (ntok >= 32)
-      const bool wrapped = n0 + lane >= p.ntok;
-      const float* wrow = p.tab + size_t(wrapped ? n0 + lane - p.ntok : 0) * kPeDm;
-      float4 wnext[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) wnext[i] = wrapped ? __ldg(reinterpret_cast<const float4*>(wrow) + i)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      for (int k = 0; k < kPeEpiSlots && i_mt < p.m_tiles; ++k) request();
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        const int wrow0 = mt * 128 + q * 32;
 #pragma unroll 1
-      for (int nt = 0; nt < 3; ++nt, ++acc) {
-        const uint32_t as = acc & 1;
-        mbar_wait(&t_full[as], (acc >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + as * 256;
-#pragma unroll 1
-        for (int c = 0; c < 16; ++c) {
-          const int col = nt * 256 + c * 16;
-          uint32_t v[16];
-          tmem_ld_x16(taddr + c * 16, v);
-          if (lane == 0) {
-            tma_store_wait_read<1>();    // every store but the previous chunk's has read its slot: refill those
-            issue_ahead();
-          }
-          float4 wcur[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) wcur[i] = wnext[i];
-          if (wrapped && col + 16 < kPeDm) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) wnext[i] = __ldg(reinterpret_cast<const float4*>(wrow + col + 16) + i);
-          }
+        for (int cc = 0; cc < 48; ++cc, ++cs) {
           const uint32_t s0 = cs & 3;
-          uint8_t* b0 = ring + s0 * kPeEpiBuf;
-          mbar_wait(&my_full[s0], (cs >> 2) & 1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t off = uint32_t(lane) * 64 + ((uint32_t(ch) ^ swz) << 4);
-            const float4 s4 = *reinterpret_cast<const float4*>(b0 + off);
-            const float4 t4 = wrapped ? wcur[ch] : s4;
-            float4 o;
-            o.x = __uint_as_float(v[4 * ch]) + t4.x; o.y = __uint_as_float(v[4 * ch + 1]) + t4.y;
-            o.z = __uint_as_float(v[4 * ch + 2]) + t4.z; o.w = __uint_as_float(v[4 * ch + 3]) + t4.w;
-            *reinterpret_cast<float4*>(b0 + off) = o;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, b0, col, wrow0);      // rows past M are clipped by the tensor map
-            tma_store_commit();
-          }
-          cs_prev = cs;
-          ++cs;
+          mbar_wait(&my_ready[s0], (cs >> 2) & 1);
+          tma_store_2d(&tmOut, ring + s0 * kPeEpiBuf, cc * 16, wrow0);      // rows past M are clipped by the tensor map
+          tma_store_commit();
+          // every store but this one has read its slot: chunk cs - 1's slot takes the request for chunk cs + 3
+          tma_store_wait_read<1>();
+          if (cs >= 1 && i_mt < p.m_tiles) request();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[as]);
       }
-      n0 += tile_step;
-      if (n0 >= p.ntok) n0 -= p.ntok;
+      tma_store_wait<0>();
     }
-    if (lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
