@@ -31,7 +31,7 @@ constexpr int kPeMaxTok = 16;                // patches per strip (8 converter t
 constexpr int kPeSW = 160;                   // frames per strip box
 constexpr int kPeSrc = 16 * kPeSW * 4;       // 10240 B per source clip and strip (16 mel rows x 160 frames, fp32)
 constexpr int kPeBuf = 2 * kPeSrc;           // 20480 B per staging slot (two sources)
-constexpr int kPeSlots = 3;                  // staging ring depth
+constexpr int kPeSlots = 3;                  // staging ring depth with mixup (two sources per slot); 6 single-source slots without
 constexpr int kPeEpiSlots = 4;               // per epilogue warp: ring of [32 rows x 16 cols] fp32 buffers
 constexpr int kPeEpiBuf = 32 * 64;
 
@@ -59,7 +59,7 @@ struct PatchEmbedSmem {
   static constexpr int kStage = kB + 65536;                 // 3 slots x 2 sources x 10240 B = 60 KB
   static constexpr int kEpi = kStage + kPeSlots * kPeBuf;   // 4 epilogue warps x 4 x 2 KB = 32 KB
   static constexpr int kMeta = kEpi + 4 * kPeEpiSlots * kPeEpiBuf;   // per staging slot: {first row, patches, start frame, last}
-  static constexpr int kBars = kMeta + 64;
+  static constexpr int kBars = kMeta + 128;
   static constexpr int kTotal = kBars + 512;
 };
 
@@ -73,28 +73,31 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   uint8_t* sB = smem + PatchEmbedSmem::kB;
   uint8_t* sStage = smem + PatchEmbedSmem::kStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PatchEmbedSmem::kBars);
-  uint64_t* st_full = bars;            // [3] staging strip landed (TMA tx)
-  uint64_t* st_empty = bars + 3;       // [3] 4 arrivals (converter warps)
-  uint64_t* b_full = bars + 6;         // [2]
-  uint64_t* b_empty = bars + 8;        // [2] tcgen05.commit
-  uint64_t* a_full = bars + 10;        // [1] 4 arrivals: A tile of this token tile is complete
-  uint64_t* a_empty = bars + 11;       // [1] commit after the tile's last MMA
-  uint64_t* t_full = bars + 12;        // [2] accumulator ready
-  uint64_t* t_empty = bars + 14;       // [2] 4 arrivals (epilogue warps)
-  uint64_t* e_full = bars + 16;        // [4 warps][4 slots] token-table chunk landed (TMA tx)
-  uint64_t* e_ready = bars + 32;       // [4 warps][4 slots] sum written into the slot (1 arrival, epilogue lane 0)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 48);
+  uint64_t* st_full = bars;            // [6] staging strip landed (TMA tx)
+  uint64_t* st_empty = bars + 6;       // [6] 4 arrivals (converter warps)
+  uint64_t* b_full = bars + 12;        // [2]
+  uint64_t* b_empty = bars + 14;       // [2] tcgen05.commit
+  uint64_t* a_full = bars + 16;        // [1] 4 arrivals: A tile of this token tile is complete
+  uint64_t* a_empty = bars + 17;       // [1] commit after the tile's last MMA
+  uint64_t* t_full = bars + 18;        // [2] accumulator ready
+  uint64_t* t_empty = bars + 20;       // [2] 4 arrivals (epilogue warps)
+  uint64_t* e_full = bars + 22;        // [4 warps][4 slots] token-table chunk landed (TMA tx)
+  uint64_t* e_ready = bars + 38;       // [4 warps][4 slots] sum written into the slot (1 arrival, epilogue lane 0)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 54);
   int4* s_meta = reinterpret_cast<int4*>(smem + PatchEmbedSmem::kMeta);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool mixing = (p.mix_perm != nullptr);
+  // staging ring: 3 slots of two sources with mixup, 6 slots of one source without (strip latency ~2 us: depth matters)
+  const uint32_t nslots = mixing ? uint32_t(kPeSlots) : uint32_t(2 * kPeSlots);
+  const uint32_t slot_bytes = mixing ? uint32_t(kPeBuf) : uint32_t(kPeSrc);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmMel);
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmTab);
     tma_prefetch_desc(&tmOut);
-    for (int s = 0; s < kPeSlots; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
+    for (int s = 0; s < 2 * kPeSlots; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
       mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
@@ -114,21 +117,20 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
   if (warp == 0) {
     // ===================== strip producer =====================
     if (lane == 0) {
-      uint32_t ss = 0;               // running staging-strip counter
+      uint32_t s = 0, ph = 0;        // staging slot and its phase
       // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
       auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
-        const uint32_t s = ss % kPeSlots;
-        mbar_wait(&st_empty[s], ((ss / kPeSlots) & 1) ^ 1);
+        mbar_wait(&st_empty[s], ph ^ 1);
         s_meta[s] = make_int4(first, cnt, ws, last);
         if (cnt == 0) {
           mbar_arrive(&st_full[s]);
         } else {
-          uint8_t* dst = sStage + s * kPeBuf;
-          mbar_arrive_expect_tx(&st_full[s], uint32_t(kPeSrc) * (mixing ? 2u : 1u));
+          uint8_t* dst = sStage + s * slot_bytes;
+          mbar_arrive_expect_tx(&st_full[s], slot_bytes);
           tma_load_3d(dst, &tmMel, &st_full[s], ws, f0, b);
           if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], ws, f0, __ldg(p.mix_perm + b));
         }
-        ++ss;
+        if (++s == nslots) { s = 0; ph ^= 1; }
       };
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
         const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
@@ -201,7 +203,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
     const int ct = threadIdx.x - 64;          // 0..127
     const int pi = ct >> 3;                   // patch inside the strip (0..15)
     const int part = ct & 7;                  // this thread converts patch columns kx = 2*part, 2*part + 1
-    uint32_t ss = 0, tiles = 0;
+    uint32_t s = 0, ph = 0, tiles = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++tiles) {
       mbar_wait(a_empty, (tiles & 1) ^ 1);    // the previous tile's MMAs have finished reading A
       {
@@ -215,9 +217,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
               *reinterpret_cast<uint4*>(sA + kb * 16384 + ct * 128 + (c << 4)) = make_uint4(0, 0, 0, 0);
         }
       }
-      for (;; ++ss) {
-        const uint32_t s = ss % kPeSlots;
-        mbar_wait(&st_full[s], (ss / kPeSlots) & 1);
+      for (;;) {
+        mbar_wait(&st_full[s], ph);
         const int4 meta = s_meta[s];          // {first tile row, patches, strip start frame, last}
         if (pi < meta.y) {
           const int arow = meta.x + pi;
@@ -225,7 +226,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           const int b = row / p.ntok, n = row - b * p.ntok;
           const float lam = mixing ? __ldg(p.mix_lam + b) : 1.f;
           const float* src =
-              reinterpret_cast<const float*>(sStage + s * kPeBuf) + (__ldg(p.patch_t + n - 2) * p.tstride - meta.z);
+              reinterpret_cast<const float*>(sStage + s * slot_bytes) + (__ldg(p.patch_t + n - 2) * p.tstride - meta.z);
           // the 8 threads of a patch split its 16 columns (2 each) and walk the 16 rows: neighbouring lanes read
           // neighbouring frames (bank-conflict free; splitting by rows would put all 8 on one bank, row pitch 160 floats)
           const int kx = 2 * part;
@@ -245,7 +246,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_empty[s]);    // this warp has read its share of the slot (and its metadata)
-        if (meta.w) { ++ss; break; }
+        if (++s == nslots) { s = 0; ph ^= 1; }
+        if (meta.w) break;
       }
       fence_proxy_async();                           // A tile written by generic stores, read by the tensor core
       __syncwarp();
