@@ -116,10 +116,13 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
 
   if (warp == 0) {
     // ===================== strip producer =====================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;        // staging slot and its phase
-      // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
-      auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
+    // The whole warp scans the kept-patch list (lane l looks at the token l places ahead: one round of loads and a ballot
+    // per strip -- a single lane chasing patch_f / patch_t entry by entry took ~1 us per strip and starved the converter);
+    // lane 0 issues the boxes.
+    uint32_t s = 0, ph = 0;        // staging slot and its phase
+    // emit one staging strip: cnt consecutive token rows starting at tile row `first` (cnt == 0: terminator)
+    auto emit = [&](int first, int cnt, int ws, int f0, int b, int last) {
+      if (lane == 0) {
         mbar_wait(&st_empty[s], ph ^ 1);
         s_meta[s] = make_int4(first, cnt, ws, last);
         if (cnt == 0) {
@@ -130,27 +133,29 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
           tma_load_3d(dst, &tmMel, &st_full[s], ws, f0, b);
           if (mixing) tma_load_3d(dst + kPeSrc, &tmMel, &st_full[s], ws, f0, __ldg(p.mix_perm + b));
         }
-        if (++s == nslots) { s = 0; ph ^= 1; }
-      };
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
-        int r = row0;
-        while (r < row_end) {
-          const int b = r / p.ntok, n = r - b * p.ntok;
-          if (n < 2) { ++r; continue; }                      // cls / dist rows carry no patch
-          const int pf0 = __ldg(p.patch_f + n - 2);
-          const int t0 = __ldg(p.patch_t + n - 2) * p.tstride, ws = t0 & ~3;
-          int cnt = 1;
-          while (cnt < kPeMaxTok && r + cnt < row_end && n + cnt < p.ntok && __ldg(p.patch_f + n + cnt - 2) == pf0) {
-            const int t2 = __ldg(p.patch_t + n + cnt - 2) * p.tstride;
-            if (t2 < t0 || t2 + 16 > ws + kPeSW) break;
-            ++cnt;
-          }
-          emit(r - row0, cnt, ws, pf0 * p.fstride, b, 0);
-          r += cnt;
-        }
-        emit(0, 0, 0, 0, 0, 1);                              // terminator: the converter closes the tile on it
       }
+      if (++s == nslots) { s = 0; ph ^= 1; }
+    };
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      const int row0 = mt * 128, row_end = min(p.M, row0 + 128);
+      int r = row0;
+      int b = r / p.ntok, n = r - b * p.ntok;
+      while (r < row_end) {
+        if (n < 2) { ++r; ++n; continue; }                 // cls / dist rows carry no patch
+        const int nl = n + lane;
+        const bool in = lane < kPeMaxTok && r + lane < row_end && nl < p.ntok;
+        const int fl = in ? __ldg(p.patch_f + nl - 2) : -1;
+        const int tl = in ? __ldg(p.patch_t + nl - 2) * p.tstride : 0;
+        const int pf0 = __shfl_sync(0xffffffffu, fl, 0), t0 = __shfl_sync(0xffffffffu, tl, 0);
+        const int ws = t0 & ~3;
+        const bool ok = in && fl == pf0 && tl >= t0 && tl + 16 <= ws + kPeSW;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int cnt = __ffs(~m) - 1;                     // leading run of patches that share the strip (>= 1)
+        emit(r - row0, cnt, ws, pf0 * p.fstride, b, 0);
+        r += cnt; n += cnt;
+        if (n >= p.ntok) { n -= p.ntok; ++b; }
+      }
+      emit(0, 0, 0, 0, 0, 1);                              // terminator: the converter closes the tile on it
     }
   } else if (warp == 10) {
     // ===================== weight producer: 12 stages [256 out x 64 k] per token tile =====================
