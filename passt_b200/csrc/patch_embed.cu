@@ -263,9 +263,9 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmMel, const __grid_const
     // Per [32 rows x 16 cols] chunk: the token-table chunk arrives by TMA (SWIZZLE_64B box, requested by this warp's
     // helper up to three chunks ahead through a 4-slot ring), the accumulator chunk by tcgen05.ld; the sum overwrites the
     // slot in place and the helper stores it by TMA.  Neither the table read nor the token store costs LSU line requests
-    // (a lane walking its own 3 KB row costs 32 per instruction; a padded transposition with coalesced accesses was slower still:
-    // profiles/r2_patch_embed_iterations.txt), and the TMA bookkeeping is off this warp: one warp per scheduler exposes every instruction's latency
-    // (~1000 clk per chunk with the bookkeeping inline).
+    // (a lane walking its own 3 KB row costs 32 per instruction; a padded transposition with coalesced accesses was
+    // slower still), and the TMA bookkeeping is off this warp: one warp per scheduler exposes every instruction's
+    // latency (~1000 clk per chunk with the bookkeeping inline).  Measurements: profiles/r2_patch_embed_iterations.txt.
     const int ew = warp - 6;
     const int q = warp & 3;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
