@@ -70,6 +70,10 @@ int passt_attn_bwd_ex(const void* qkv, const void* out, const void* d_out, const
 /* forward schedule: 2 (default) = ping-pong kernel, one CTA per SM with two query tiles in flight (attn_fwd2.cu);
  * 1 = two CTAs per SM, one query tile each (attn_fwd.cu).  Same results. */
 void passt_attn_fwd_set_variant(int variant);
+/* attention backward kernel: 1 (default) = eight compute warps (64-query column halves), 2 = sixteen (32-query quarters);
+ * environment PASST_B200_ATTN_BWD.  Same results. */
+void passt_attn_bwd_set_variant(int variant);
+int passt_attn_bwd_get_variant(void);
 /* programmatic dependent launch of the hot-path kernels (1 = default; environment PASST_B200_PDL=0 turns it off) */
 void passt_set_pdl(int enable);
 int passt_get_pdl(void);

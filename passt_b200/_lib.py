@@ -66,6 +66,8 @@ _SIGS = {
     "passt_set_pdl": (None, [i32]),
     "passt_get_pdl": (i32, []),
     "passt_attn_fwd_set_variant": (None, [i32]),
+    "passt_attn_bwd_set_variant": (None, [i32]),
+    "passt_attn_bwd_get_variant": (i32, []),
     "passt_attn_bwd_prepare": (i32, [vp, i32, i32, i32, vp]),
     "passt_attn_bwd_dsum_ptr": (vp, [vp, i32, i32, i32]),
     "passt_attn_bwd_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]),
@@ -136,7 +138,7 @@ def check(rc: int, what: str):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_LAUNCHES = {"passt_adamw_step": 2, "passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_attn_bwd_ex": 3, "passt_attn_bwd_prepare": 0, "passt_attn_bwd_dsum_ptr": 0, "passt_set_pdl": 0, "passt_set_sm_limit": 0, "passt_get_sm_limit": 0, "passt_get_pdl": 0, "passt_attn_fwd_set_variant": 0, "passt_mel_workspace_bytes": 0, "passt_loss_workspace_bytes": 0,
+_LAUNCHES = {"passt_adamw_step": 2, "passt_attn_debug_timeline": 0, "passt_attn_bwd_debug_timeline": 0, "passt_gemm_set_2cta": 0, "passt_gemm_debug_desc": 0, "passt_head_bwd": 2, "passt_attn_bwd": 3, "passt_attn_bwd_ex": 3, "passt_attn_bwd_prepare": 0, "passt_attn_bwd_dsum_ptr": 0, "passt_set_pdl": 0, "passt_set_sm_limit": 0, "passt_get_sm_limit": 0, "passt_get_pdl": 0, "passt_attn_fwd_set_variant": 0, "passt_attn_bwd_set_variant": 0, "passt_attn_bwd_get_variant": 0, "passt_mel_workspace_bytes": 0, "passt_loss_workspace_bytes": 0,
              "passt_attn_bwd_workspace_bytes": 0}
 _launch_counter = 0
 

@@ -394,7 +394,348 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant 2 (PASST_B200_ATTN_BWD=2): the same schedule with SIXTEEN compute warps -- four per TMEM lane quadrant, each
+// owning a 32-query column quarter of the score tiles instead of a 64-query half.  The math phase between the S^T/dP^T
+// MMAs and the dQ/dV/dK MMAs is a serial stretch of the step (tensor pipe idle); with two warps per scheduler its
+// tcgen05.ld / MUFU / shared-memory latencies are exposed, with four they overlap.  Layout differences: the packed P^T
+// / dS^T operand of quarter qc starts at its own first score column (TMEM column qc*32, 16 columns), so a warp only
+// overwrites score columns it has read itself; K / V staging, the dQ drain and the dK / dV epilogue are split in 16-
+// column pieces.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwd2Threads = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 compute
+
+// 32 lanes x 16 values -> lanes l and l + 16 end up with the sum over all lanes of value (l & 15)
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < n / 2) {
+        const float send = up ? v[j] : v[j + n / 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+        v[j] = (up ? v[j + n / 2] : v[j]) + recv;
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+__global__ void __launch_bounds__(kBwd2Threads, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmdO,
+                 const __grid_constant__ CUtensorMap tmdQKV, const __grid_constant__ CUtensorMap tmdQacc,
+                 const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* sKV = smem + AttnBwdSmem::kKV;
+  uint8_t* sQdO = smem + AttnBwdSmem::kQdO;
+  uint8_t* sdST = smem + AttnBwdSmem::kdST;
+  uint8_t* sdQ = smem + AttnBwdSmem::kdQ;
+  float* sVec = reinterpret_cast<float*>(smem + AttnBwdSmem::kVec);
+  float* sBias = reinterpret_cast<float*>(smem + AttnBwdSmem::kBias);   // [0,768): dK sums, [768,1536): dV sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnBwdSmem::kBars);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2]  tcgen05.commit after the item's last MMA
+  uint64_t* qdo_full = bars + 4;     // [2]
+  uint64_t* qdo_empty = bars + 6;    // [2]
+  uint64_t* sdp_full = bars + 8;     // [1]
+  uint64_t* pds_full = bars + 9;     // [1] 512 arrivals
+  uint64_t* dq_full = bars + 10;     // [1]
+  uint64_t* dkv_full = bars + 11;    // [1]
+  uint64_t* kv_ready = bars + 12;    // [1] 512 arrivals: K, V copied into TMEM
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+  constexpr int kCT = 512;           // compute threads
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_q = (p.N + kTile - 1) / kTile;
+  const int C = p.H * kBHd;
+  const int qcols_last = ((p.N - (n_q - 1) * kTile + 31) / 32) * 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQKV); tma_prefetch_desc(&tmdQacc);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, kCT);
+    mbar_init(dq_full, 1);
+    mbar_init(dkv_full, 1);
+    mbar_init(kv_ready, kCT);
+    fence_barrier_init();
+  }
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) sBias[i] = 0.f;
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_gate();
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
+                 tdQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0, n = 0;
+      for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+        const int kvt = it % p.n_kvt, h = (it / p.n_kvt) % p.H, b = it / (p.n_kvt * p.H);
+        const uint32_t kb = n & 1;
+        mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[kb], 2 * 16384);
+        tma_load_3d(sKV + kb * 32768, &tmQKV, &kv_full[kb], C + h * kBHd, kvt * kTile, b);
+        tma_load_3d(sKV + kb * 32768 + 16384, &tmQKV, &kv_full[kb], 2 * C + h * kBHd, kvt * kTile, b);
+        for (int i = 0; i < n_q; ++i, ++g) {
+          const uint32_t s = g & 1;
+          mbar_wait(&qdo_empty[s], ((g >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&qdo_full[s], 2 * 16384 + 2 * 512);
+          tma_load_3d(sQdO + s * 32768, &tmQKV, &qdo_full[s], h * kBHd, i * kTile, b);
+          tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, &qdo_full[s], h * kBHd, i * kTile, b);
+          const size_t voff = (size_t(b) * p.H + h) * p.Npad + size_t(i) * kTile;
+          bulk_load_1d(sVec + s * 256, p.lse + voff, 512, &qdo_full[s]);
+          bulk_load_1d(sVec + s * 256 + 128, p.Dsum + voff, 512, &qdo_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t id_q = make_idesc_bf16(128, 64, 1, 1);
+    uint64_t bQk[2], bdOk[2], bQmn[2], bdOmn[2], bKmn[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t aQ = smem_u32(sQdO + s * 32768), adO = aQ + 16384;
+      bQk[s] = make_smem_desc_sw128(aQ, 16, 1024);          // Q  as K-major B  (S^T = K Q^T)
+      bdOk[s] = make_smem_desc_sw128(adO, 16, 1024);        // dO as K-major B  (dP^T = V dO^T)
+      bQmn[s] = make_smem_desc_sw128(aQ, 8192, 1024);       // Q  as MN-major B (dK += dS^T Q)
+      bdOmn[s] = make_smem_desc_sw128(adO, 8192, 1024);     // dO as MN-major B (dV += P^T dO)
+      bKmn[s] = make_smem_desc_sw128(smem_u32(sKV + s * 32768), 8192, 1024);   // K as MN-major B (dQ = dS K)
+    }
+    const uint64_t bdST = make_smem_desc_sw128(smem_u32(sdST), 16384, 1024);   // dS^T as MN-major A (dQ = dS K)
+    const uint32_t id_s_last = make_idesc_bf16(128, qcols_last, 0, 0);
+    uint32_t g = 0, n = 0;
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+      const uint32_t kb = n & 1;
+      mbar_wait(kv_ready, n & 1);
+      tc_fence_after();
+      for (int i = 0; i < n_q; ++i, ++g) {
+        const uint32_t s = g & 1;
+        mbar_wait(&qdo_full[s], (g >> 1) & 1);
+        tc_fence_after();
+        const bool last_q = (i == n_q - 1);
+        const uint32_t ids = last_q ? id_s_last : id_s;
+        const int n_qk = last_q ? qcols_last / 16 : 8;      // 16-query contraction steps of dV / dK
+        if (elect_one()) {
+          const uint64_t qk = s ? bQk[1] : bQk[0], dok = s ? bdOk[1] : bdOk[0];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tS, tK + k * 8, qk + uint64_t(k * 2), ids, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tdP, tV + k * 8, dok + uint64_t(k * 2), ids, k > 0);
+          tc_commit(sdp_full);
+        }
+        __syncwarp();
+        mbar_wait(pds_full, g & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t qmn = s ? bQmn[1] : bQmn[0], domn = s ? bdOmn[1] : bdOmn[0];
+          const uint64_t kmn = kb ? bKmn[1] : bKmn[0];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // contraction = keys: dS^T rows; A is MN-major with two 64-query groups
+            umma_bf16_ss(tdQ, bdST + uint64_t(k * 128), kmn + uint64_t(k * 128), id_q, k > 0);
+          tc_commit(dq_full);           // dQ first: the compute warps drain it while dV / dK accumulate
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // contraction = queries; 16 queries = 8 TMEM columns of packed bf16,
+            if (k < n_qk)               // quarter k/2 starts at column (k/2)*32
+              umma_bf16_ts(tdV, tS + (k >> 1) * 32 + (k & 1) * 8, domn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < n_qk)
+              umma_bf16_ts(tdK, tdP + (k >> 1) * 32 + (k & 1) * 8, qmn + uint64_t(k * 128), id_kv, (i > 0 || k > 0));
+          tc_commit(&qdo_empty[s]);
+          if (i == n_q - 1) {
+            tc_commit(dkv_full);
+            tc_commit(&kv_empty[kb]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int cw = warp - 2;            // 0..15
+    const int q = warp & 3;             // TMEM lane quadrant
+    const int qc = cw >> 2;             // which 32-column quarter of the 128 query columns this warp handles
+    const int hc = qc >> 1;             // 64-query half the quarter belongs to (shared-memory operand groups)
+    const int r = q * 32 + lane;        // row inside the tile (key row for S^T/dP^T, query row for dQ)
+    const int ct = threadIdx.x - 64;    // 0..511
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    // K (quarters 0, 1) and V (quarters 2, 3) rows of item n, 32 of the 64 dims each: swizzled smem -> packed bf16 in TMEM
+    auto stage_kv = [&](uint32_t n) {
+      const uint32_t kb = n & 1;
+      mbar_wait(&kv_full[kb], (n >> 1) & 1);
+      const uint8_t* src = sKV + kb * 32768 + (qc < 2 ? 0 : 16384);
+      const int half = qc & 1;
+      uint32_t kv[16];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int cc = half * 4 + ch;
+        const uint4 u = *reinterpret_cast<const uint4*>(src + r * 128 + ((cc ^ (r & 7)) << 4));
+        kv[ch * 4] = u.x; kv[ch * 4 + 1] = u.y; kv[ch * 4 + 2] = u.z; kv[ch * 4 + 3] = u.w;
+      }
+      tmem_st_x16((qc < 2 ? tK : tV) + half * 16 + lane_addr, kv);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(kv_ready);
+    };
+    uint32_t g = 0, n = 0;
+    if (blockIdx.x < p.total_items) stage_kv(0);
+    for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, ++n) {
+      const int kvt = it % p.n_kvt, h = (it / p.n_kvt) % p.H, b = it / (p.n_kvt * p.H);
+      const int kv0 = kvt * kTile;
+      const bool has_next = (it + int(gridDim.x) < p.total_items);
+      for (int i = 0; i < n_q; ++i, ++g) {
+        const int q0 = i * kTile;
+        const float* s_lse = sVec + (g & 1) * 256;     // log2-domain LSE of this query tile (TMA bulk copy)
+        const float* s_D = s_lse + 128;
+        mbar_wait(&qdo_full[g & 1], (g >> 1) & 1);     // lse / D landed with the Q / dO tiles
+        mbar_wait(sdp_full, g & 1);
+        tc_fence_after();
+        const int q_cols = (i == n_q - 1) ? qcols_last : kTile;
+        const int col0 = qc * 32;
+        if (col0 < q_cols) {                 // trimmed last query tile: whole quarters drop out (warp-uniform)
+          uint32_t pp[16], dd2[16];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t sv[16], dv[16];
+            tmem_ld_x16(tS + lane_addr + col0 + sub * 16, sv);
+            tmem_ld_x16(tdP + lane_addr + col0 + sub * 16, dv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(s_lse + col0 + sub * 16 + e);
+              const float4 d4 = *reinterpret_cast<const float4*>(s_D + col0 + sub * 16 + e);
+              const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, -l4.x));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -l4.y));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e + 2]), p.scale_log2, -l4.z));
+              const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e + 3]), p.scale_log2, -l4.w));
+              const int o = sub * 8 + (e >> 1);
+              pp[o] = pack_bf16(p0, p1);
+              pp[o + 1] = pack_bf16(p2, p3);
+              dd2[o] = pack_bf16(p0 * (__uint_as_float(dv[e]) - d4.x), p1 * (__uint_as_float(dv[e + 1]) - d4.y));
+              dd2[o + 1] = pack_bf16(p2 * (__uint_as_float(dv[e + 2]) - d4.z), p3 * (__uint_as_float(dv[e + 3]) - d4.w));
+            }
+          }
+          // both 16-column loads of this quarter are complete: its first 16 columns take the packed operands
+          tmem_st_x16(tS + lane_addr + col0, pp);      // A operand of dV += P^T dO
+          tmem_st_x16(tdP + lane_addr + col0, dd2);    // A operand of dK += dS^T Q
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {   // dS^T also goes to smem: dQ = dS K reads it MN-major
+            const int ch = (qc & 1) * 4 + gq;   // 16-byte chunk inside this 64-query half
+            const uint32_t off = hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(sdST + off) =
+                make_uint4(dd2[gq * 4], dd2[gq * 4 + 1], dd2[gq * 4 + 2], dd2[gq * 4 + 3]);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(pds_full);
+        if (i == n_q - 1 && has_next) stage_kv(n + 1);
+        // ---- drain dQ_i (rows = queries) -> fp32 staging -> TMA reduce-add into the accumulation buffer
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        if (ct == 0) tma_store_wait_read<0>();   // staging (dQ of the previous step / dK,dV of the previous item) was read
+        named_bar_sync(1, kCT);
+        {
+          uint32_t v[16];
+          tmem_ld_x16(tdQ + lane_addr + qc * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = (qc & 1) * 4 + j;
+            float4 o = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                   __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+            *reinterpret_cast<float4*>(sdQ + hc * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = o;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1, kCT);
+        if (ct == 0) {
+          tma_reduce_add_3d(&tmdQacc, sdQ, h * kBHd, q0, b);
+          tma_reduce_add_3d(&tmdQacc, sdQ + 16384, h * kBHd + 32, q0, b);
+          tma_store_commit();
+        }
+      }
+      // ---- item epilogue: dK (scaled), dV -> bf16 -> staging (dQ staging buffer) -> TMA store
+      mbar_wait(dkv_full, n & 1);
+      tc_fence_after();
+      if (ct == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kCT);
+      {
+        uint32_t vv[16], kk[16];
+        tmem_ld_x16(tdV + lane_addr + qc * 16, vv);
+        tmem_ld_x16(tdK + lane_addr + qc * 16, kk);
+        tmem_ld_wait();
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          const int ch = qc * 2 + gq;
+          const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(vv[gq * 8 + 0]), __uint_as_float(vv[gq * 8 + 1]));
+          o.y = pack_bf16(__uint_as_float(vv[gq * 8 + 2]), __uint_as_float(vv[gq * 8 + 3]));
+          o.z = pack_bf16(__uint_as_float(vv[gq * 8 + 4]), __uint_as_float(vv[gq * 8 + 5]));
+          o.w = pack_bf16(__uint_as_float(vv[gq * 8 + 6]), __uint_as_float(vv[gq * 8 + 7]));
+          *reinterpret_cast<uint4*>(sdQ + off) = o;                                  // dV tile
+          o.x = pack_bf16(__uint_as_float(kk[gq * 8 + 0]) * p.scale, __uint_as_float(kk[gq * 8 + 1]) * p.scale);
+          o.y = pack_bf16(__uint_as_float(kk[gq * 8 + 2]) * p.scale, __uint_as_float(kk[gq * 8 + 3]) * p.scale);
+          o.z = pack_bf16(__uint_as_float(kk[gq * 8 + 4]) * p.scale, __uint_as_float(kk[gq * 8 + 5]) * p.scale);
+          o.w = pack_bf16(__uint_as_float(kk[gq * 8 + 6]) * p.scale, __uint_as_float(kk[gq * 8 + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(sdQ + 16384 + off) = o;                          // dK tile
+        }
+        if (p.dbias != nullptr) {
+          const bool valid = (kv0 + r < p.N);
+          float cv[16], ck[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            cv[e] = valid ? __bfloat162float(__float2bfloat16(__uint_as_float(vv[e]))) : 0.f;
+            ck[e] = valid ? __bfloat162float(__float2bfloat16(__uint_as_float(kk[e]) * p.scale)) : 0.f;
+          }
+          const float sv = warp_colsum16(cv, lane);
+          const float sk = warp_colsum16(ck, lane);
+          if (lane < 16) {
+            atomicAdd(&sBias[768 + h * kBHd + qc * 16 + lane], sv);    // shared-memory partials, flushed once per CTA
+            atomicAdd(&sBias[h * kBHd + qc * 16 + lane], sk);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar_sync(1, kCT);
+      if (ct == 0) {
+        tma_store_3d(&tmdQKV, sdQ + 16384, C + h * kBHd, kv0, b);   // dK
+        tma_store_3d(&tmdQKV, sdQ, 2 * C + h * kBHd, kv0, b);       // dV
+        tma_store_commit();
+      }
+    }
+    if (ct == 0) tma_store_wait<0>();
+    if (p.dbias != nullptr) {
+      named_bar_sync(1, kCT);
+      for (int i = ct; i < 2 * 768; i += kCT) {
+        const float v = sBias[i];
+        if (v != 0.f) atomicAdd(p.dbias + C + i, v);     // K third at [C, 2C), V third at [2C, 3C)
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 long long* g_attn_bwd_timeline = nullptr;
+int g_attn_bwd_variant = -1;      // 1: eight compute warps (default), 2: sixteen; -1: read PASST_B200_ATTN_BWD on first use
+
 
 // D[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]     (one warp per token, 8 lanes per head)
 __global__ void __launch_bounds__(256)
@@ -472,6 +813,9 @@ attn_dq_pack_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d
 extern "C" {
 
 void passt_attn_bwd_debug_timeline(void* buf) { pb::g_attn_bwd_timeline = reinterpret_cast<long long*>(buf); }
+/* 1: eight compute warps, 2: sixteen compute warps (32-query column quarters) */
+void passt_attn_bwd_set_variant(int v) { pb::g_attn_bwd_variant = (v == 2) ? 2 : 1; }
+int passt_attn_bwd_get_variant(void) { return pb::g_attn_bwd_variant; }
 
 size_t passt_attn_bwd_workspace_bytes(int B, int N, int H) {
   const size_t npad = size_t((N + 127) / 128) * 128;
@@ -543,9 +887,20 @@ int passt_attn_bwd_ex(const void* qkv, const void* o, const void* dO, const floa
   p.dq_acc = dq_acc;
   p.dbias = dbias_qkv;
   p.timeline = pb::g_attn_bwd_timeline;
-  PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal + kSmemAlignSlack, attn_bwd_kernel);
+  if (g_attn_bwd_variant < 0) {
+    const char* e = getenv("PASST_B200_ATTN_BWD");
+    g_attn_bwd_variant = (e != nullptr && e[0] == '2') ? 2 : 1;
+  }
   const int grid = p.total_items < g_sm_limit ? p.total_items : g_sm_limit;
-  PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal + kSmemAlignSlack, st, tmQKV, tmdO, tmdQKV, tmdQacc, p);
+  if (g_attn_bwd_variant == 2) {
+    PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal + kSmemAlignSlack, attn_bwd2_kernel);
+    PB_LAUNCH(attn_bwd2_kernel, grid, kBwd2Threads, AttnBwdSmem::kTotal + kSmemAlignSlack, st, tmQKV, tmdO, tmdQKV,
+              tmdQacc, p);
+  } else {
+    PB_SET_SMEM_ONCE(AttnBwdSmem::kTotal + kSmemAlignSlack, attn_bwd_kernel);
+    PB_LAUNCH(attn_bwd_kernel, grid, kBwdThreads, AttnBwdSmem::kTotal + kSmemAlignSlack, st, tmQKV, tmdO, tmdQKV,
+              tmdQacc, p);
+  }
   {
     if (C % 256 != 0) return PB_ERR_BAD_ARG;
     const int rows = B * N;

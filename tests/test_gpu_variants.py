@@ -4,7 +4,8 @@
     fp32 softmax-attention reference, for token counts with even / odd / single query-tile counts;
   * programmatic dependent launch on / off;
   * residual adds fused into the proj / fc2 GEMM epilogues on / off;
-  * attention-backward D = rowsum(dO o O) fused into the proj-dgrad GEMM epilogue on / off.
+  * attention-backward D = rowsum(dO o O) fused into the proj-dgrad GEMM epilogue on / off;
+  * attention backward with eight vs sixteen compute warps.
 """
 import pytest
 import torch
@@ -58,6 +59,48 @@ def test_attention_forward_variants_agree(N, ramp):
         assert torch.isinf(lse[:, :, N:]).all()
     assert relerr(outs[2][0], outs[1][0]) < 4e-3          # same per-row arithmetic; bf16 output rounding at most
     assert relerr(outs[3][0], outs[1][0]) < 8e-3          # a side-wide redo moves the reference of rows that did not need it: 1-2 bf16 ulps
+
+
+@pytest.mark.parametrize("N", [474, 353, 130, 1190, 64])
+def test_attention_backward_variants_agree(N):
+    """attn_bwd_kernel (eight compute warps) vs attn_bwd2_kernel (sixteen, 32-query column quarters) vs torch autograd of
+    the fp32 softmax attention on the same bf16 inputs."""
+    from passt_b200 import _lib as L
+    lib = L.load()
+    B, H = 3, 12
+    C = H * 64
+    torch.manual_seed(N + 1)
+    qkv = (torch.randn(B, N, 3 * C, device=DEV) * 1.2).bfloat16()
+    dO = (torch.randn(B, N, C, device=DEV) * 0.5).bfloat16()
+    npad = ((N + 127) // 128) * 128
+    o = torch.zeros(B, N, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, npad, device=DEV)
+    L.call("passt_attn_fwd", L.ptr(qkv), L.ptr(o), L.ptr(lse), B, N, H, 0.125, L.stream_ptr())
+    ws = torch.empty(lib.passt_attn_bwd_workspace_bytes(B, N, H), dtype=torch.uint8, device=DEV)
+    outs = {}
+    try:
+        for variant in (1, 2):
+            lib.passt_attn_bwd_set_variant(variant)
+            dqkv = torch.zeros_like(qkv)
+            dbias = torch.zeros(3 * C, device=DEV)
+            L.call("passt_attn_bwd", L.ptr(qkv), L.ptr(o), L.ptr(dO), L.ptr(lse), L.ptr(dqkv), L.ptr(dbias), L.ptr(ws), B, N,
+                   H, 0.125, L.stream_ptr())
+            torch.cuda.synchronize()
+            outs[variant] = (dqkv, dbias)
+    finally:
+        lib.passt_attn_bwd_set_variant(1)
+    x = qkv.float().requires_grad_(True)
+    ref_o, _ = _attn_ref(x, H)
+    ref_o.backward(dO.float())
+    for variant in (1, 2):
+        dqkv, dbias = outs[variant]
+        for part, name in enumerate("qkv"):
+            sl = slice(part * C, (part + 1) * C)
+            assert relerr(dqkv[:, :, sl], x.grad[:, :, sl]) < 2e-2, (variant, name)
+        assert relerr(dbias, x.grad.sum((0, 1))) < 2e-2, variant
+    # same per-element arithmetic and the same MMA contraction order: identical up to the order of the fp32 dQ reduce-adds
+    assert relerr(outs[2][0], outs[1][0]) < 4e-3
+    assert relerr(outs[2][1], outs[1][1]) < 2e-3
 
 
 def _small_train_net(seed=0):
