@@ -68,7 +68,8 @@ float* passt_attn_bwd_dsum_ptr(void* workspace, int B, int N, int H);
 int passt_attn_bwd_ex(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv,
                       float* d_bias_qkv, void* workspace, int B, int N, int H, float scale, int flags, void* stream);
 /* forward schedule: 2 (default) = ping-pong kernel, one CTA per SM with two query tiles in flight (attn_fwd2.cu);
- * 1 = two CTAs per SM, one query tile each (attn_fwd.cu).  Same results. */
+ * 4 = the same with the next Q K^T issued as soon as a tile's scores are in registers; 3 = ping-pong with two softmax
+ * threads per row (attn_fwd3.cu); 1 = two CTAs per SM, one query tile each (attn_fwd.cu).  Same results. */
 void passt_attn_fwd_set_variant(int variant);
 /* attention backward kernel: 1 (default) = eight compute warps (64-query column halves), 2 = sixteen (32-query quarters);
  * environment PASST_B200_ATTN_BWD.  Same results. */

@@ -355,12 +355,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 long long* g_attn_timeline = nullptr;
 
 // attn_fwd2.cu: ping-pong variant (one CTA per SM, two query tiles in flight)
-int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st);
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool early_s,
+                     cudaStream_t st);
 // attn_fwd3.cu: ping-pong with two softmax threads per query row (16 softmax warps)
 int launch_attn_fwd3(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st);
 int g_attn_fwd_variant = [] {
-  const char* e = getenv("PASST_B200_ATTN_FWD");     // 2 (default): ping-pong; 3: ping-pong, 2 threads per row; 1: 2 CTAs per SM
-  return (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '3') ? 3 : 2;
+  // 2 (default): ping-pong; 4: ping-pong, next Q K^T issued as soon as the scores are in registers; 3: ping-pong, 2 threads
+  // per row; 1: 2 CTAs per SM
+  const char* e = getenv("PASST_B200_ATTN_FWD");
+  return (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '3') ? 3 : (e != nullptr && e[0] == '4') ? 4 : 2;
 }();
 
 }  // namespace pb
@@ -370,15 +373,15 @@ extern "C" {
 void passt_attn_debug_timeline(void* buf) { pb::g_attn_timeline = reinterpret_cast<long long*>(buf); }
 
 // 2 (default): ping-pong kernel (attn_fwd2.cu); 1: the two-CTAs-per-SM kernel of this file
-void passt_attn_fwd_set_variant(int v) { pb::g_attn_fwd_variant = (v == 1 || v == 3) ? v : 2; }
+void passt_attn_fwd_set_variant(int v) { pb::g_attn_fwd_variant = (v == 1 || v == 3 || v == 4) ? v : 2; }
 
 
 // qkv: bf16 [B, N, 3*H*64]; out: bf16 [B, N, H*64]; lse: fp32 [B, H, Npad], Npad = 128*ceil(N/128), log2 domain
 int passt_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, void* stream) {
   using namespace pb;
   if (B <= 0 || N <= 0 || H <= 0) return PB_ERR_BAD_ARG;
-  if (g_attn_fwd_variant == 2 && g_attn_timeline == nullptr)
-    return launch_attn_fwd2(qkv, out, lse, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
+  if ((g_attn_fwd_variant == 2 || g_attn_fwd_variant == 4) && g_attn_timeline == nullptr)
+    return launch_attn_fwd2(qkv, out, lse, B, N, H, scale, g_attn_fwd_variant == 4, reinterpret_cast<cudaStream_t>(stream));
   if (g_attn_fwd_variant == 3 && g_attn_timeline == nullptr)
     return launch_attn_fwd3(qkv, out, lse, B, N, H, scale, reinterpret_cast<cudaStream_t>(stream));
   const int C = H * kHd;

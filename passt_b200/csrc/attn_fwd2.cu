@@ -53,7 +53,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));   // * 2^round(x)
 }
 
-template <bool kPrefetch, bool kPolyExp>
+template <bool kPrefetch, bool kPolyExp, bool kEarlyS>
 __global__ void __launch_bounds__(k2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                  const AttnFwd2Params p) {
@@ -69,6 +69,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint64_t* s_full = bars + 16;        // [2 sides]
   uint64_t* p_full = bars + 18;        // [2 sides] 128 arrivals
   uint64_t* pv_done = bars + 20;       // [2 sides]
+  uint64_t* s_used = bars + 22;        // [2 sides] 128 arrivals (kEarlyS): every score of S_X(j) is in registers
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +82,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
     for (int s = 0; s < k2KvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); mbar_init(&s_used[x], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_holder);
@@ -178,15 +181,25 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const uint32_t s = t % k2KvStages;
         const bool last_j = (j + 1 == n_kv);
         for (int x = 0; x < nx; ++x) {
+          // next scores of this side first: its softmax threads can start on them while P_X V runs
+          auto issue_next_s = [&]() {
+            if (!last_j) {
+              issue_s(x, slot, t + 1, j + 2 == n_kv);
+            } else if (has_next && (x == 0 || next_has_b)) {
+              wait_q((slot ^ 1) * 2 + x);
+              issue_s(x, slot ^ 1, t + 1, n_kv == 1);
+            }
+          };
+          if (kEarlyS) {
+            // S_X(j) has been read into registers (one 32-column chunk of exp2 work is still ahead of the softmax
+            // threads): the Q K^T round trip of the next tile runs under that chunk instead of after it
+            mbar_wait(&s_used[x], tcount[x] & 1);
+            tc_fence_after();
+            issue_next_s();
+          }
           mbar_wait(&p_full[x], tcount[x] & 1);     // P_X(j) is in TMEM, S_X(j) consumed
           tc_fence_after();
-          // next scores of this side first: its softmax threads can start on them while P_X V runs
-          if (!last_j) {
-            issue_s(x, slot, t + 1, j + 2 == n_kv);
-          } else if (has_next && (x == 0 || next_has_b)) {
-            wait_q((slot ^ 1) * 2 + x);
-            issue_s(x, slot ^ 1, t + 1, n_kv == 1);
-          }
+          if (!kEarlyS) issue_next_s();
           const uint32_t aV = aKV0 + s * (2 * k2Tile * k2Hd * 2) + k2Tile * k2Hd * 2;
           const uint64_t dv = make_smem_desc_sw128(aV, 8192, 1024);
           const int n_pv = last_j ? cols_last / 16 : 8;   // 16 keys per MMA
@@ -288,6 +301,19 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
               tmem_ld_wait();
             }
             uint32_t (&v)[32] = vv[kPrefetch ? (c & 1) : 0];
+            if (kEarlyS && c == n_chunks - 1) {
+              // every score of this tile is now in registers.  Unless the guard below is going to ask for a second pass
+              // over S (same maximum, same test), hand the S columns back to the MMA warp before the last chunk's exp2s
+              float cm = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (full_tile || c * 32 + i < kv_valid) cm = fmaxf(cm, __uint_as_float(v[i]));
+              const float tile_max_pre = fmaxf(fmaxf(mx0, mx1), cm) * p.scale_log2;
+              if (!__any_sync(0xffffffffu, tile_max_pre - m_used > kGuardTh)) {
+                tc_fence_before();
+                mbar_arrive(&s_used[x]);
+              }
+            }
             uint32_t pk[16];
             if (full_tile) {
 #pragma unroll
@@ -385,7 +411,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st) {
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool early,
+                     cudaStream_t st) {
   const int C = H * k2Hd;
   CUtensorMap tmQKV, tmO;
   int rc;
@@ -409,15 +436,18 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int N, int H
     const char* e = getenv("PASST_B200_ATTN_POLYEXP");      // default off; 1: every 4th exp2 on the FMA pipe
     return e != nullptr && e[0] == '1';
   }();
-#define PB_FWD2(PF, PE)                                                                                       \
+#define PB_FWD2(PF, PE, ES)                                                                                   \
   do {                                                                                                        \
-    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<PF, PE>);                       \
-    PB_LAUNCH((attn_fwd2_kernel<PF, PE>), grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, p); \
+    PB_SET_SMEM_ONCE(AttnFwd2Smem::kTotal + kSmemAlignSlack, attn_fwd2_kernel<PF, PE, ES>);                   \
+    PB_LAUNCH((attn_fwd2_kernel<PF, PE, ES>), grid, k2Threads, AttnFwd2Smem::kTotal + kSmemAlignSlack, st, tmQKV, tmO, \
+              p);                                                                                             \
   } while (0)
-  if (prefetch && poly) PB_FWD2(true, true);
-  else if (prefetch) PB_FWD2(true, false);
-  else if (poly) PB_FWD2(false, true);
-  else PB_FWD2(false, false);
+  if (early && prefetch) PB_FWD2(true, false, true);
+  else if (early) PB_FWD2(false, false, true);
+  else if (prefetch && poly) PB_FWD2(true, true, false);
+  else if (prefetch) PB_FWD2(true, false, false);
+  else if (poly) PB_FWD2(false, true, false);
+  else PB_FWD2(false, false, false);
 #undef PB_FWD2
   return 0;
 }
