@@ -191,7 +191,9 @@ class GraphedTrainStep:
 
 class GraphedInference:
     """CUDA-graph replay of the inference path (waveform -> mel (eval) -> PaSST forward): ~110 launches become one.
-    ``logits = step(wave)``; the returned tensor is the graph's static output buffer (valid until the next call)."""
+    ``logits = step(wave)``; the returned tensor is the graph's static output buffer (valid until the next call).
+    The fp32 parameters other than the GEMM weights (LayerNorm, biases, positional embeddings, head) are read in place;
+    after changing weights call ``resync()``."""
 
     def __init__(self, mel, net, example_wave: torch.Tensor, warmup: int = 2):
         if not example_wave.is_cuda:
@@ -222,6 +224,17 @@ class GraphedInference:
         with torch.cuda.graph(self.graph):
             self.logits, self.features = self._body()
         torch.cuda.synchronize()
+
+    def resync(self):
+        """Call after the parameters were changed behind the graph's back (``load_state_dict``, SWA averaging into this
+        net, manual edits): re-casts the bf16 GEMM-operand copies the captured forward reads (the capture holds no
+        refresh of its own: the warm-up passes had already cleared the cache's dirty flag)."""
+        depth = len(self.net.blocks)
+        P = dict(self.net.named_parameters())
+        wnames = ["patch_embed.proj.weight"] + [f"blocks.{i}.{w}.weight" for i in range(depth)
+                                                for w in ("attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2")]
+        with torch.cuda.device(self.wave.device):
+            self.net._wcache.refresh_all([P[n] for n in wnames])
 
     def _body(self):
         with torch.no_grad():

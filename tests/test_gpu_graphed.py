@@ -72,3 +72,30 @@ def test_graphed_step_matches_eager():
         xa = mel_a.eval()(waves[0]).unsqueeze(1)
         la, lb = net_a(xa)[0], net_b(xa)[0]
         assert ((la - lb).abs().max() / la.abs().max()).item() < 2e-2
+
+
+def test_graphed_inference_matches_eager_and_resyncs():
+    """GraphedInference (the cfg1 / cfg4 bench path) == the eager eval forward, also after the weights were edited and
+    resync() re-cast the bf16 operand copies."""
+    from passt_b200.graphed import GraphedInference
+    B = 3
+    mel, net = _make(3)
+    mel.eval(); net.eval()
+    torch.manual_seed(1)
+    waves = [0.1 * torch.randn(B, 320000, device=DEV) for _ in range(3)]
+
+    def eager(w):
+        with torch.no_grad():
+            return net(mel(w).unsqueeze(1))[0].clone()
+
+    g = GraphedInference(mel, net, waves[0])
+    for w in waves:
+        assert torch.equal(g(w), eager(w))
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.02)
+    ref = eager(waves[1])                 # the eager forward notices the in-place edit (version counter) and re-casts
+    g.resync()
+    got = g(waves[1]).clone()
+    assert torch.equal(got, ref)
+    assert not torch.equal(got, g(waves[2]))
